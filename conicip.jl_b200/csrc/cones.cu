@@ -1,0 +1,396 @@
+// Cone kernels K5-K8: Nesterov-Todd scaling, block apply, max step, Jordan product / division,
+// and the scaled panel Atil = F^-T A.  R rows are elementwise (vectorised grid-stride); each
+// Q cone is handled by one warp (or one 256-thread group for very large cones) with warp
+// reductions.  Replaces src/ConicIP.jl:165-194 (nestod_soc), :212-270 (maxstep_rp/soc),
+// :305-345 (drp/xrp/dsoc/xsoc), :571-665 (closures) and src/blockmatrices.jl:107-131 (Block*x).
+#include <math_constants.h>
+
+#include "kernels.cuh"
+#include "../../include/conicip_b200.h"
+
+namespace cip {
+
+namespace {
+
+// ---- group reductions: G == 32 -> one warp per cone; G == 256 -> one CTA per cone
+template <int G>
+__device__ __forceinline__ double group_sum(double v, double* sm) {
+  v = warp_sum(v);
+  if (G == 32) return v;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < G / 32; ++i) t += sm[i];
+  return t;
+}
+
+template <int G>
+__device__ __forceinline__ bool q_cone_of(const ConeDesc& c, int& ci, int& off, int& dim, int& lid) {
+  const int per_block = blockDim.x / G;
+  const int qi = blockIdx.x * per_block + threadIdx.x / G;
+  lid = threadIdx.x % G;
+  if (qi >= c.nq) return false;   // G==256: whole block exits together; G==32: whole warp
+  ci = c.qlist[qi];
+  off = c.off[ci];
+  dim = c.off[ci + 1] - off;
+  return true;
+}
+
+// order-preserving map double -> uint64 for atomicMin
+__device__ __forceinline__ unsigned long long dkey(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// ================================================================= NT scaling
+__global__ void nt_r_kernel(ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
+                            Scaling Fi, double* __restrict__ lambda) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
+    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+    const double f = sqrt(s[i] / v[i]);          // Diagonal(sqrt.(yI./xI)), src/ConicIP.jl:598
+    F.a[i] = f;
+    F.b[i] = 0.0;
+    Fi.a[i] = 1.0 / f;
+    Fi.b[i] = 0.0;
+    lambda[i] = f * v[i];
+  }
+}
+
+__global__ void nt_kind_kernel(ConeDesc c, Scaling F, Scaling Fi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.ncones) return;
+  if (c.type[i] == CIP_CONE_R) {
+    F.kind[i] = CIP_BLK_DIAG;  Fi.kind[i] = CIP_BLK_DIAG;  F.D[i] = 0.0;  Fi.D[i] = 0.0;
+  } else if (c.type[i] == CIP_CONE_Q) {
+    F.kind[i] = CIP_BLK_WOODBURY;  Fi.kind[i] = CIP_BLK_WOODBURY;   // D set by nt_q_kernel
+  }
+}
+
+template <int G>
+__global__ void nt_q_kernel(ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
+                            Scaling Fi, double* __restrict__ lambda) {
+  __shared__ double sm[8];
+  int ci, off, dim, lid;
+  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
+  const double* z = v + off;     // nestod_soc(z = v_I, s = s_I), src/ConicIP.jl:599
+  const double* sv = s + off;
+  double zz = 0, ss = 0;
+  for (int i = lid; i < dim; i += G) { zz += z[i] * z[i]; ss += sv[i] * sv[i]; }
+  zz = group_sum<G>(zz, sm);
+  ss = group_sum<G>(ss, sm);
+  const double qfz = 2 * z[0] * z[0] - zz;       // QF, src/ConicIP.jl:160
+  const double qfs = 2 * sv[0] * sv[0] - ss;
+  const double beta = sqrt(sqrt(qfs / qfz));     // (QF(s)/QF(z))^(1/4)
+  const double rz = sqrt(qfz), rs = sqrt(qfs);
+  double zs = 0;
+  for (int i = lid; i < dim; i += G) zs += (z[i] / rz) * (sv[i] / rs);
+  zs = group_sum<G>(zs, sm);
+  const double gamma = sqrt((1 + zs) / 2);
+  const double inv2g = 1.0 / (2.0 * gamma);
+  // w = (s + Jz)/(2 gamma); w1 += 1; w *= sqrt(2 beta)/sqrt(2 w1)
+  const double w1 = inv2g * (sv[0] / rs + z[0] / rz) + 1.0;
+  const double scal = sqrt(2 * beta) / sqrt(2 * w1);
+  double wv = 0, bib = 0;
+  for (int i = lid; i < dim; i += G) {
+    const double zi = z[i] / rz, si = sv[i] / rs;
+    const double w = (i == 0) ? w1 * scal : (inv2g * (si - zi)) * scal;
+    const double a = (i == 0) ? -beta : beta;
+    F.a[off + i] = a;
+    F.b[off + i] = w;
+    const double ia = 1.0 / a;                   // Woodbury inverse: W = inv(A), X = W*B
+    Fi.a[off + i] = ia;
+    Fi.b[off + i] = ia * w;
+    wv += w * z[i];
+    bib += w * (ia * w);
+  }
+  wv = group_sum<G>(wv, sm);
+  bib = group_sum<G>(bib, sm);
+  for (int i = lid; i < dim; i += G) lambda[off + i] = F.a[off + i] * z[i] + F.b[off + i] * wv;  // F*v
+  if (lid == 0) {
+    F.D[ci] = 1.0;
+    Fi.D[ci] = 1.0 / (-1.0 - bib);               // Z = inv(-inv(D) - B'X), D = 1
+  }
+}
+
+// generic inverse of a flattened scaling (used by cip_factor / cip_set_scaling)
+__global__ void inv_diag_kernel(ConeDesc c, Scaling F, Scaling Fi) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
+    const double ia = 1.0 / F.a[i];
+    Fi.a[i] = ia;
+    Fi.b[i] = (F.kind[c.row_cone[i]] == CIP_BLK_WOODBURY) ? ia * F.b[i] : 0.0;
+  }
+}
+__global__ void inv_wood_kernel(ConeDesc c, Scaling F, Scaling Fi) {
+  // one warp per cone (any type); only kind-1 blocks do work
+  const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ci >= c.ncones) return;
+  if (lane == 0) Fi.kind[ci] = F.kind[ci];
+  if (F.kind[ci] != CIP_BLK_WOODBURY) {
+    if (lane == 0) Fi.D[ci] = 0.0;
+    return;
+  }
+  const int off = c.off[ci], dim = c.off[ci + 1] - off;
+  double bib = 0;
+  for (int i = lane; i < dim; i += 32) bib += F.b[off + i] * (F.b[off + i] / F.a[off + i]);
+  bib = warp_sum(bib);
+  if (lane == 0) Fi.D[ci] = 1.0 / (-1.0 / F.D[ci] - bib);
+}
+
+// ================================================================= block apply
+__global__ void apply_diag_kernel(int m, const double* __restrict__ a, const double* __restrict__ x,
+                                  double* __restrict__ y) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) y[i] = a[i] * x[i];
+}
+__global__ void apply_wood_kernel(ConeDesc c, Scaling F, const double* __restrict__ x, double* __restrict__ y) {
+  const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ci >= c.ncones || F.kind[ci] != CIP_BLK_WOODBURY) return;
+  const int off = c.off[ci], dim = c.off[ci + 1] - off;
+  double bx = 0;
+  for (int i = lane; i < dim; i += 32) bx += F.b[off + i] * x[off + i];
+  bx = warp_sum(bx) * F.D[ci];
+  for (int i = lane; i < dim; i += 32) y[off + i] += F.b[off + i] * bx;   // A*x + B*(D*(B'x))
+}
+
+// ================================================================= Jordan product / division
+__global__ void prod_r_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
+                              double* __restrict__ o, int divide) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
+    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+    o[i] = divide ? x[i] / y[i] : x[i] * y[i];   // drp! / xrp!, src/ConicIP.jl:305-315
+  }
+}
+template <int G>
+__global__ void prod_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
+                              double* __restrict__ o) {
+  __shared__ double sm[8];
+  int ci, off, dim, lid;
+  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
+  const double* xp = x + off;
+  const double* yp = y + off;
+  double d = 0;
+  for (int i = lid; i < dim; i += G) d += xp[i] * yp[i];
+  d = group_sum<G>(d, sm);
+  const double x0 = xp[0], y0 = yp[0];
+  for (int i = lid; i < dim; i += G) o[off + i] = (i == 0) ? d : x0 * yp[i] + y0 * xp[i];   // xsoc!, :340-345
+}
+template <int G>
+__global__ void div_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
+                             double* __restrict__ o) {
+  // o = arrow(y)^-1 x   (dsoc!(y=x_arg, x=y_arg, o), src/ConicIP.jl:317-338)
+  __shared__ double sm[8];
+  int ci, off, dim, lid;
+  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
+  const double* num = x + off;   // reference's "y" (x1, xb)
+  const double* arr = y + off;   // reference's "x" (y1, yb)
+  double ybyb = 0, ybxb = 0;
+  for (int i = lid; i < dim; i += G) {
+    if (i > 0) { ybyb += arr[i] * arr[i]; ybxb += arr[i] * num[i]; }
+  }
+  ybyb = group_sum<G>(ybyb, sm);
+  ybxb = group_sum<G>(ybxb, sm);
+  const double y1 = arr[0], x1 = num[0];
+  const double alpha = y1 * y1 - ybyb;
+  const double b1 = (-x1 / alpha) + ybxb / (y1 * alpha);
+  const double b2 = 1.0 / y1;
+  for (int i = lid; i < dim; i += G)
+    o[off + i] = (i == 0) ? (y1 * x1 - ybxb) / alpha : arr[i] * b1 + num[i] * b2;
+}
+
+// ================================================================= max step
+__global__ void maxstep_init_kernel(unsigned long long* key) { *key = dkey(CUDART_INF); }
+__global__ void maxstep_r_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
+                                 double d_scale, unsigned long long* key) {
+  double mn = CUDART_INF;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
+    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+    if (d) {
+      const double di = d[i] / d_scale;
+      if (di > 0) mn = fmin(mn, x[i] / di);                     // maxstep_rp, :212-225
+    } else {
+      mn = fmin(mn, x[i] > 0 ? 0.0 : -1.0 + x[i]);              // :227-240
+    }
+  }
+  mn = warp_min(mn);
+  if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
+}
+template <int G>
+__global__ void maxstep_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
+                                 double d_scale, unsigned long long* key) {
+  __shared__ double sm[8];
+  int ci, off, dim, lid;
+  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
+  const double* xp = x + off;
+  double res;
+  if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
+    double nn = 0;
+    for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
+    nn = group_sum<G>(nn, sm);
+    const double al = sqrt(nn) - xp[0];
+    res = al < 0 ? 0.0 : -1.0 - al;
+  } else {                                                       // maxstep_soc(x, d), :242-262
+    const double* dp = d + off;
+    double xx = 0;
+    for (int i = lid; i < dim; i += G) xx += xp[i] * xp[i];
+    xx = group_sum<G>(xx, sm);
+    const double gam = 2 * xp[0] * xp[0] - xx;
+    const double rg = sqrt(gam);
+    const double d0 = -(dp[0] / d_scale);
+    double xd = 0;
+    for (int i = lid; i < dim; i += G) xd += (xp[i] / rg) * (-(dp[i] / d_scale));
+    xd = group_sum<G>(xd, sm);
+    const double xb0 = xp[0] / rg;
+    const double beta = 2 * xb0 * d0 - xd;
+    const double rho1 = beta / rg;
+    const double mu = (beta + d0) / (xb0 + 1);
+    double r2 = 0;
+    for (int i = lid; i < dim; i += G) {
+      if (i > 0) {
+        const double r = -(dp[i] / d_scale) - mu * (xp[i] / rg);
+        r2 += r * r;
+      }
+    }
+    r2 = group_sum<G>(r2, sm);
+    const double al = sqrt(r2) / rg - rho1;
+    res = al < 0 ? CUDART_INF : 1.0 / al;
+  }
+  if (lid == 0 && res < CUDART_INF) atomicMin(key, dkey(res));
+}
+
+// ================================================================= scaled panel  Atil = F^-T A
+__global__ void __launch_bounds__(256)
+scale_panel_diag_kernel(const double* __restrict__ At4, double* __restrict__ Atil4, int ld,
+                        const double* __restrict__ ia) {
+  const int kq = blockIdx.x;
+  const double2 s0 = *reinterpret_cast<const double2*>(ia + 4 * kq);
+  const double2 s1 = *reinterpret_cast<const double2*>(ia + 4 * kq + 2);
+  const size_t base = (size_t)kq * ld * 4;
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < ld; j += gridDim.y * blockDim.x) {
+    const double2* in = reinterpret_cast<const double2*>(At4 + base + (size_t)j * 4);
+    double2 v0 = __ldg(in), v1 = __ldg(in + 1);
+    v0.x *= s0.x; v0.y *= s0.y; v1.x *= s1.x; v1.y *= s1.y;
+    double2* out = reinterpret_cast<double2*>(Atil4 + base + (size_t)j * 4);
+    out[0] = v0;
+    out[1] = v1;
+  }
+}
+__global__ void __launch_bounds__(128)
+scale_panel_wood_kernel(ConeDesc c, Scaling Fi, const double* __restrict__ At4, double* __restrict__ Atil4,
+                        int ld, int ncols) {
+  // block (column chunk, cone): thread per column j of A; adds D * b (b' A[:, j]) over the cone's rows
+  const int ci = c.qlist[blockIdx.x];
+  if (Fi.kind[ci] != CIP_BLK_WOODBURY) return;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  const int off = c.off[ci], end = c.off[ci + 1];
+  double dot = 0;
+  for (int k = off; k < end; ++k) dot += Fi.b[k] * At4[q4_index(j, k, ld)];
+  dot *= Fi.D[ci];
+  for (int k = off; k < end; ++k) Atil4[q4_index(j, k, ld)] += Fi.b[k] * dot;
+}
+
+inline int nblocks(int n, int per) {
+  int b = (n + per - 1) / per;
+  return b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b);
+}
+
+}  // namespace
+
+#define Q_DISPATCH(kernel, ...)                                                   \
+  do {                                                                            \
+    if (c.nq > 0) {                                                               \
+      if (c.max_q_dim > 1024) {                                                   \
+        kernel<256><<<c.nq, 256, 0, st>>>(__VA_ARGS__);                           \
+      } else {                                                                    \
+        kernel<32><<<(c.nq + 7) / 8, 256, 0, st>>>(__VA_ARGS__);                  \
+      }                                                                           \
+      CIP_CHECK_LAUNCH();                                                         \
+    }                                                                             \
+  } while (0)
+
+int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling F, Scaling Fi, double* lambda,
+                    cudaStream_t st) {
+  if (c.ns > 0) {
+    set_error("S cones: NT scaling on device not available in this build");
+    return -2;
+  }
+  if (c.m == 0) return 0;
+  nt_kind_kernel<<<(c.ncones + 255) / 256, 256, 0, st>>>(c, F, Fi);
+  CIP_CHECK_LAUNCH();
+  nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
+  CIP_CHECK_LAUNCH();
+  Q_DISPATCH(nt_q_kernel, c, v, s, F, Fi, lambda);
+  return 0;
+}
+
+int cone_invert_scaling(const ConeDesc& c, Scaling F, Scaling Fi, cudaStream_t st) {
+  if (c.m == 0) return 0;
+  inv_diag_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, F, Fi);
+  CIP_CHECK_LAUNCH();
+  inv_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, F, Fi);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+int cone_apply(const ConeDesc& c, Scaling F, const double* x, double* y, cudaStream_t st) {
+  if (c.m == 0) return 0;
+  apply_diag_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c.m, F.a, x, y);
+  CIP_CHECK_LAUNCH();
+  if (c.nq + c.ns > 0) {   // only non-R cones can carry a Woodbury block
+    apply_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, F, x, y);
+    CIP_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
+  if (c.ns > 0) { set_error("S cones: cone_prod not available in this build"); return -2; }
+  if (c.m == 0) return 0;
+  prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
+  CIP_CHECK_LAUNCH();
+  Q_DISPATCH(prod_q_kernel, c, x, y, o);
+  return 0;
+}
+
+int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
+  if (c.ns > 0) { set_error("S cones: cone_div not available in this build"); return -2; }
+  if (c.m == 0) return 0;
+  prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
+  CIP_CHECK_LAUNCH();
+  Q_DISPATCH(div_q_kernel, c, x, y, o);
+  return 0;
+}
+
+int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, double* partial,
+                 int npartial, double* result, cudaStream_t st) {
+  (void)partial; (void)npartial;
+  if (c.ns > 0) { set_error("S cones: maxstep not available in this build"); return -2; }
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(result);
+  maxstep_init_kernel<<<1, 1, 0, st>>>(key);
+  CIP_CHECK_LAUNCH();
+  if (c.m == 0) return 0;
+  maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
+  CIP_CHECK_LAUNCH();
+  Q_DISPATCH(maxstep_q_kernel, c, x, d, d_scale, key);
+  return 0;
+}
+
+int cone_scale_panel(const ConeDesc& c, Scaling Fi, const double* At4, double* Atil4, int ld, int m_pad,
+                     int ncols, cudaStream_t st) {
+  if (m_pad == 0) return 0;
+  dim3 grid(m_pad / 4, (ld + 255) / 256 > 8 ? 8 : (ld + 255) / 256);
+  scale_panel_diag_kernel<<<grid, 256, 0, st>>>(At4, Atil4, ld, Fi.a);
+  CIP_CHECK_LAUNCH();
+  if (c.nq > 0) {
+    dim3 g2(c.nq, (ncols + 127) / 128);
+    scale_panel_wood_kernel<<<g2, 128, 0, st>>>(c, Fi, At4, Atil4, ld, ncols);
+    CIP_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace cip

@@ -1,0 +1,750 @@
+// The KKT engine handle and the C ABI of include/conicip_b200.h.
+//
+// LEVEL 1 (cip_create)  : upload Q, A, G once, re-laid out in the Q4 layout (A transposed, so the
+//                         contraction index of every tensor-core product is the interleaved one).
+// LEVEL 2 (cip_factor)  : Atil = F^-T A (cone kernel) -> H = Q + Atil'Atil (DMMA SYRK, TMA fed)
+//                         -> [NCCL all-reduce of the partial Gram matrices] -> blocked Cholesky
+//                         -> Schur complement on G (same DMMA tiles).
+// LEVEL 3 (cip_solve)   : the pivot algebra of src/kktsolvers.jl:324-332 on the resident data.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/conicip_b200.h"
+#include "kernels.cuh"
+#include "nccl_dl.h"
+
+namespace cip {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace cip
+
+using namespace cip;
+
+namespace {
+constexpr int NV = 8;   // n-length work vectors
+constexpr int MV = 10;  // m-length work vectors
+constexpr int PV = 6;   // p-length work vectors
+}  // namespace
+
+struct cip_engine {
+  int n = 0, m = 0, p = 0, n_pad = 0, m_pad = 0, p_pad = 0, ncones = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cip_options opt{};
+  // matrices (Q4 layout)
+  double *At4 = nullptr, *Atil4 = nullptr, *Qq4 = nullptr, *H4 = nullptr, *Winv = nullptr;
+  double *G4 = nullptr, *Z4 = nullptr, *S4 = nullptr, *Sbase4 = nullptr, *WinvS = nullptr;
+  GemmOperand mapAtil{}, mapZ{};
+  CholPlan cholH{}, cholS{};
+  int* info = nullptr;  // [2] device
+  // cones
+  std::vector<int> h_type, h_off;
+  int *d_type = nullptr, *d_off = nullptr, *d_rowcone = nullptr, *d_qlist = nullptr, *d_slist = nullptr;
+  ConeDesc cd{};
+  Scaling F{}, Fi{};
+  bool have_scaling = false, have_factor = false;
+  // work vectors
+  double* nv[NV] = {};
+  double* mv[MV] = {};
+  double* pv[PV] = {};
+  double* partial = nullptr;
+  int partial_cap = 0;
+  double* scalar = nullptr;  // device scratch scalars [8]
+  // NCCL
+  void* comm = nullptr;
+  int nranks = 1, rank = 0;
+  // stats
+  cip_stats_t st{};
+  cudaEvent_t ev[8] = {};
+  size_t bytes = 0;
+  bool need_sync = false;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(cip_engine* h, T** p, size_t count, bool zero = true) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CIP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  if (zero) CIP_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), h->stream));
+  h->bytes += count * sizeof(T);
+  return 0;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// stage an input vector (host or device) into an internal zero-padded device buffer
+int stage_in(cip_engine* h, double* dst, const double* src, size_t n) {
+  if (n == 0) return 0;
+  if (!src) {
+    set_error("null input vector");
+    return -1;
+  }
+  CIP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDefault, h->stream));
+  return 0;
+}
+int stage_out(cip_engine* h, double* dst, const double* src, size_t n) {
+  if (n == 0 || !dst) return 0;
+  CIP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDefault, h->stream));
+  if (!is_device_ptr(dst)) h->need_sync = true;
+  return 0;
+}
+int finish(cip_engine* h) {
+  if (h->need_sync) {
+    CIP_CUDA(cudaStreamSynchronize(h->stream));
+    h->need_sync = false;
+  }
+  return 0;
+}
+
+int check(cip_handle h) {
+  if (!h) {
+    set_error("null handle");
+    return -1;
+  }
+  CIP_CUDA(cudaSetDevice(h->device));
+  return 0;
+}
+
+int allreduce(cip_engine* h, double* buf, size_t count) {
+  if (!h->comm) return 0;
+  const NcclApi* api = nccl_api();
+  if (!api) return -1;
+  int r = api->AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+  if (r != 0) {
+    set_error("ncclAllReduce failed: %s", api->GetErrorString(r));
+    return -1;
+  }
+  return 0;
+}
+
+int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, const double* fb, const double* fD,
+                          const double* fR) {
+  (void)fR;
+  if (!kind || !fa) {
+    set_error("cip_factor/cip_set_scaling: kind and fa are required");
+    return -1;
+  }
+  std::vector<int> hk(h->ncones);
+  if (is_device_ptr(kind)) {
+    CIP_CUDA(cudaMemcpy(hk.data(), kind, sizeof(int) * h->ncones, cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(hk.data(), kind, sizeof(int) * h->ncones);
+  }
+  bool any_w = false;
+  for (int i = 0; i < h->ncones; ++i) {
+    if (hk[i] == CIP_BLK_VECCONG) {
+      set_error("VecCongurance (S cone) scaling blocks are not available in this build");
+      return -2;
+    }
+    if (hk[i] != CIP_BLK_DIAG && hk[i] != CIP_BLK_WOODBURY) {
+      set_error("unknown scaling block kind %d for cone %d", hk[i], i);
+      return -1;
+    }
+    any_w |= (hk[i] == CIP_BLK_WOODBURY);
+  }
+  CIP_CUDA(cudaMemcpyAsync(h->F.kind, hk.data(), sizeof(int) * h->ncones, cudaMemcpyHostToDevice, h->stream));
+  CIP_CUDA(cudaStreamSynchronize(h->stream));  // hk goes out of scope
+  CIP_TRY(stage_in(h, h->F.a, fa, h->m));
+  if (any_w) {
+    if (!fb || !fD) {
+      set_error("SymWoodbury blocks need fb and fD");
+      return -1;
+    }
+    CIP_TRY(stage_in(h, h->F.b, fb, h->m));
+    CIP_TRY(stage_in(h, h->F.D, fD, h->ncones));
+  } else {
+    CIP_TRY(fill_zero(h->F.b, h->m, h->stream));
+    CIP_TRY(fill_zero(h->F.D, h->ncones, h->stream));
+  }
+  CIP_TRY(cone_invert_scaling(h->cd, h->F, h->Fi, h->stream));
+  h->have_scaling = true;
+  return 0;
+}
+
+int form_H(cip_engine* h) {
+  if (!h->have_scaling) {
+    set_error("no scaling set (call cip_factor / cip_set_scaling / cip_nt_scaling first)");
+    return -1;
+  }
+  cudaStream_t s = h->stream;
+  CIP_CUDA(cudaEventRecord(h->ev[0], s));
+  if (h->m_pad > 0) CIP_TRY(cone_scale_panel(h->cd, h->Fi, h->At4, h->Atil4, h->n_pad, h->m_pad, h->n, s));
+  CIP_CUDA(cudaEventRecord(h->ev[1], s));
+  const double* cin = (h->rank == 0) ? h->Qq4 : nullptr;
+  if (h->m_pad > 0) {
+    GemmArgs a{};
+    a.lower = 1; a.ntm = a.ntn = h->n_pad / TILE; a.sym = 1;
+    a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = h->m_pad / 32;
+    a.Cin = cin; a.Cout = h->H4; a.ldc = h->n_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
+    CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, s));
+  } else {
+    if (cin) CIP_TRY(vec_copy(h->H4, cin, (size_t)h->n_pad * h->n_pad, s));
+    else CIP_TRY(fill_zero(h->H4, (size_t)h->n_pad * h->n_pad, s));
+  }
+  CIP_CUDA(cudaEventRecord(h->ev[2], s));
+  if (h->comm) CIP_TRY(allreduce(h, h->H4, (size_t)h->n_pad * h->n_pad));
+  if (h->opt.reg_delta != 0.0) CIP_TRY(add_diag_q4(h->H4, h->n_pad, 0, h->n, h->opt.reg_delta, 0, s));
+  CIP_CUDA(cudaEventRecord(h->ev[3], s));
+  h->st.syrk_flops = (double)h->m * (double)h->n * (double)h->n;
+  return 0;
+}
+
+int factor_H(cip_engine* h) {
+  cudaStream_t s = h->stream;
+  CIP_TRY(chol_factor(h->cholH, s));
+  CIP_CUDA(cudaEventRecord(h->ev[4], s));
+  if (h->p > 0) {
+    // Z = G L^-T by a right-looking blocked substitution on the DMMA tiles, S = Z Z', S = Ls Ls'
+    CIP_TRY(vec_copy(h->Z4, h->G4, (size_t)h->p_pad * h->n_pad, s));
+    const int np = h->n_pad / TILE, ptiles = h->p_pad / TILE;
+    for (int jb = 0; jb < np; ++jb) {
+      const int j0 = jb * TILE;
+      GemmArgs t{};
+      t.lower = 0; t.ntm = ptiles; t.ntn = 1; t.sym = 0;
+      t.x_row0 = 0; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = TILE / 32;
+      t.Cin = nullptr; t.Cout = h->Z4; t.ldc = h->p_pad; t.c_row0 = 0; t.c_col0 = j0; t.alpha = 1.0;
+      CIP_TRY(launch_gemm_nt(h->mapZ, h->cholH.mapWinv, t, s));
+      const int rem = np - jb - 1;
+      if (rem == 0) break;
+      GemmArgs u{};
+      u.lower = 0; u.ntm = ptiles; u.ntn = rem; u.sym = 0;
+      u.x_row0 = 0; u.y_row0 = j0 + TILE; u.x_kq0 = j0 / 4; u.y_kq0 = j0 / 4; u.nk = TILE / 32;
+      u.Cin = h->Z4; u.Cout = h->Z4; u.ldc = h->p_pad; u.c_row0 = 0; u.c_col0 = j0 + TILE; u.alpha = -1.0;
+      CIP_TRY(launch_gemm_nt(h->mapZ, h->cholH.mapH, u, s));
+    }
+    GemmArgs a{};
+    a.lower = 1; a.ntm = a.ntn = ptiles; a.sym = 1;
+    a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = h->n_pad / 32;
+    a.Cin = h->Sbase4; a.Cout = h->S4; a.ldc = h->p_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
+    CIP_TRY(launch_gemm_nt(h->mapZ, h->mapZ, a, s));
+    CIP_TRY(chol_factor(h->cholS, s));
+  }
+  CIP_CUDA(cudaEventRecord(h->ev[5], s));
+  int hinfo[2] = {0, 0};
+  CIP_CUDA(cudaMemcpyAsync(hinfo, h->info, sizeof(hinfo), cudaMemcpyDeviceToHost, s));
+  CIP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->st.ms_scale = ms;
+  cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->st.ms_syrk = ms;
+  cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->st.ms_allreduce = ms;
+  cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->st.ms_chol = ms;
+  cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->st.ms_schur = ms;
+  cudaGetLastError();
+  h->st.chol_flops = (double)h->n * h->n * h->n / 3.0;
+  h->st.factors++;
+  h->have_factor = true;
+  if (hinfo[0] != 0) {
+    set_error("Cholesky of H failed: non-positive pivot at column %d", hinfo[0]);
+    return hinfo[0];
+  }
+  if (hinfo[1] != 0) {
+    set_error("Cholesky of the Schur complement failed: non-positive pivot at row %d", hinfo[1]);
+    return h->n + hinfo[1];
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* cip_last_error(void) { return cip::g_err; }
+int cip_version(void) { return 100; }
+
+int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+               const double* G, int ldg, int ncones, const int* cone_type, const int* cone_dim,
+               const cip_options* opts) {
+  if (!out || n <= 0 || m < 0 || p < 0 || ncones < 0) {
+    set_error("cip_create: bad dimensions n=%d m=%d p=%d ncones=%d", n, m, p, ncones);
+    return -1;
+  }
+  cip_engine* h = new cip_engine();
+  *out = nullptr;
+  if (opts) memcpy(&h->opt, opts, std::min<size_t>(sizeof(cip_options), (size_t)opts->struct_size));
+  else h->opt.device = -1;
+  if (h->opt.device < 0) CIP_CUDA(cudaGetDevice(&h->device));
+  else h->device = h->opt.device;
+  CIP_CUDA(cudaSetDevice(h->device));
+  {
+    cudaDeviceProp prop;
+    CIP_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major != 10) {
+      set_error("conicip_b200 requires an sm_100a device (found sm_%d%d); there is no fallback path", prop.major,
+                prop.minor);
+      delete h;
+      return -3;
+    }
+  }
+  CIP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = h->stream;
+  for (auto& e : h->ev) {
+    CIP_CUDA(cudaEventCreate(&e));
+    CIP_CUDA(cudaEventRecord(e, h->stream));
+  }
+  h->n = n; h->m = m; h->p = p; h->ncones = ncones;
+  h->n_pad = round_up(n, TILE);
+  h->m_pad = round_up(m, 32);
+  h->p_pad = p > 0 ? round_up(p, TILE) : 0;
+
+  // ---- cones
+  h->h_type.assign(cone_type, cone_type + ncones);
+  h->h_off.assign(ncones + 1, 0);
+  std::vector<int> rowcone(m), qlist, slist;
+  int maxq = 0, maxs = 0;
+  for (int i = 0; i < ncones; ++i) {
+    if (cone_dim[i] <= 0) {
+      set_error("cone %d has non-positive dimension", i);
+      return -1;
+    }
+    h->h_off[i + 1] = h->h_off[i] + cone_dim[i];
+    if (h->h_off[i + 1] > m) break;
+    for (int r = h->h_off[i]; r < h->h_off[i + 1]; ++r) rowcone[r] = i;
+    if (cone_type[i] == CIP_CONE_Q) { qlist.push_back(i); maxq = std::max(maxq, cone_dim[i]); }
+    else if (cone_type[i] == CIP_CONE_S) { slist.push_back(i); maxs = std::max(maxs, cone_dim[i]); }
+    else if (cone_type[i] != CIP_CONE_R) {
+      set_error("unknown cone type %d", cone_type[i]);
+      return -1;
+    }
+  }
+  if (h->h_off[ncones] != m) {
+    set_error("cone dimensions sum to %d but A has %d rows", h->h_off[ncones], m);
+    return -1;
+  }
+  CIP_TRY(dev_alloc(h, &h->d_type, ncones));
+  CIP_TRY(dev_alloc(h, &h->d_off, ncones + 1));
+  CIP_TRY(dev_alloc(h, &h->d_rowcone, m));
+  CIP_TRY(dev_alloc(h, &h->d_qlist, qlist.size()));
+  CIP_TRY(dev_alloc(h, &h->d_slist, slist.size()));
+  if (ncones) CIP_CUDA(cudaMemcpy(h->d_type, h->h_type.data(), sizeof(int) * ncones, cudaMemcpyHostToDevice));
+  CIP_CUDA(cudaMemcpy(h->d_off, h->h_off.data(), sizeof(int) * (ncones + 1), cudaMemcpyHostToDevice));
+  if (m) CIP_CUDA(cudaMemcpy(h->d_rowcone, rowcone.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
+  if (!qlist.empty())
+    CIP_CUDA(cudaMemcpy(h->d_qlist, qlist.data(), sizeof(int) * qlist.size(), cudaMemcpyHostToDevice));
+  if (!slist.empty())
+    CIP_CUDA(cudaMemcpy(h->d_slist, slist.data(), sizeof(int) * slist.size(), cudaMemcpyHostToDevice));
+  h->cd.m = m; h->cd.ncones = ncones; h->cd.type = h->d_type; h->cd.off = h->d_off;
+  h->cd.row_cone = h->d_rowcone; h->cd.qlist = h->d_qlist; h->cd.nq = (int)qlist.size();
+  h->cd.slist = h->d_slist; h->cd.ns = (int)slist.size(); h->cd.max_q_dim = maxq; h->cd.max_s_ord = maxs;
+  for (Scaling* S : {&h->F, &h->Fi}) {
+    CIP_TRY(dev_alloc(h, &S->kind, ncones));
+    CIP_TRY(dev_alloc(h, &S->a, h->m_pad + 4));
+    CIP_TRY(dev_alloc(h, &S->b, h->m_pad + 4));
+    CIP_TRY(dev_alloc(h, &S->D, ncones));
+  }
+
+  // ---- matrices
+  const size_t nn = (size_t)h->n_pad * h->n_pad;
+  const size_t mn = (size_t)h->m_pad * h->n_pad;
+  CIP_TRY(dev_alloc(h, &h->At4, mn));
+  CIP_TRY(dev_alloc(h, &h->Atil4, mn));
+  CIP_TRY(dev_alloc(h, &h->Qq4, nn));
+  CIP_TRY(dev_alloc(h, &h->H4, nn));
+  CIP_TRY(dev_alloc(h, &h->Winv, (size_t)h->n_pad * TILE));
+  CIP_TRY(dev_alloc(h, &h->info, 2));
+  cudaStream_t s = h->stream;
+
+  // Q
+  if (h->opt.q_kind == 0) {
+    if (!Q) { set_error("Q is null"); return -1; }
+    if (is_device_ptr(Q)) {
+      CIP_TRY(pack_rows_q4(h->Qq4, h->n_pad, Q, ldq, n, n, h->n_pad, h->n_pad, s));
+    } else {
+      // chunk columns through a staging buffer
+      const int chunk = std::max(4, std::min(n, (int)((256u << 20) / ((size_t)n * 8)) / 4 * 4));
+      double* stg = nullptr;
+      CIP_CUDA(cudaMalloc(&stg, (size_t)n * chunk * 8));
+      for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int nc = std::min(chunk, n - c0);
+        CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)n * 8, Q + (size_t)c0 * ldq, (size_t)ldq * 8, (size_t)n * 8, nc,
+                                   cudaMemcpyHostToDevice, s));
+        // columns c0.. -> k range; write quads (c0/4 ..)
+        CIP_TRY(pack_rows_q4(h->Qq4 + (size_t)(c0 / 4) * h->n_pad * 4, h->n_pad, stg, n, n, nc, h->n_pad,
+                             round_up(nc, 4), s));
+        CIP_CUDA(cudaStreamSynchronize(s));
+      }
+      cudaFree(stg);
+    }
+  } else if (h->opt.q_kind == 1) {
+    if (!Q) { set_error("Q (diagonal) is null"); return -1; }
+    double* dq = nullptr;
+    CIP_CUDA(cudaMalloc(&dq, sizeof(double) * n));
+    CIP_CUDA(cudaMemcpyAsync(dq, Q, sizeof(double) * n, cudaMemcpyDefault, s));
+    CIP_TRY(set_diag_vec_q4(h->Qq4, h->n_pad, n, dq, s));
+    CIP_CUDA(cudaStreamSynchronize(s));
+    cudaFree(dq);
+  }
+  CIP_TRY(add_diag_q4(h->Qq4, h->n_pad, n, h->n_pad, 1.0, 1, s));  // identity on the padding
+
+  // A (transposed into Q4: rows = columns of A)
+  if (m > 0) {
+    if (!A) { set_error("A is null"); return -1; }
+    if (is_device_ptr(A)) {
+      CIP_TRY(pack_trans_q4(h->At4, h->n_pad, 0, A, lda, m, h->m_pad, n, s));
+    } else {
+      const int chunk = std::max(1, std::min(n, (int)((512u << 20) / ((size_t)m * 8))));
+      double* stg = nullptr;
+      CIP_CUDA(cudaMalloc(&stg, (size_t)m * chunk * 8));
+      for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int nc = std::min(chunk, n - c0);
+        CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)m * 8, A + (size_t)c0 * lda, (size_t)lda * 8, (size_t)m * 8, nc,
+                                   cudaMemcpyHostToDevice, s));
+        CIP_TRY(pack_trans_q4(h->At4, h->n_pad, c0, stg, m, m, h->m_pad, nc, s));
+        CIP_CUDA(cudaStreamSynchronize(s));
+      }
+      cudaFree(stg);
+    }
+    CIP_TRY(make_q4_tensor_map(&h->mapAtil.map, h->Atil4, h->n_pad, h->m_pad / 4));
+  }
+  CIP_TRY(chol_make_plan(&h->cholH, h->H4, h->n_pad, h->Winv, h->info));
+
+  // G
+  if (p > 0) {
+    if (!G) { set_error("G is null"); return -1; }
+    const size_t pn = (size_t)h->p_pad * h->n_pad;
+    CIP_TRY(dev_alloc(h, &h->G4, pn));
+    CIP_TRY(dev_alloc(h, &h->Z4, pn));
+    CIP_TRY(dev_alloc(h, &h->S4, (size_t)h->p_pad * h->p_pad));
+    CIP_TRY(dev_alloc(h, &h->Sbase4, (size_t)h->p_pad * h->p_pad));
+    CIP_TRY(dev_alloc(h, &h->WinvS, (size_t)h->p_pad * TILE));
+    double* stg = nullptr;
+    const double* gsrc = G;
+    int gld = ldg;
+    if (!is_device_ptr(G)) {
+      CIP_CUDA(cudaMalloc(&stg, (size_t)p * n * 8));
+      CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)p * 8, G, (size_t)ldg * 8, (size_t)p * 8, n, cudaMemcpyHostToDevice, s));
+      gsrc = stg;
+      gld = p;
+    }
+    CIP_TRY(pack_rows_q4(h->G4, h->p_pad, gsrc, gld, p, n, h->p_pad, h->n_pad, s));
+    CIP_CUDA(cudaStreamSynchronize(s));
+    if (stg) cudaFree(stg);
+    CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, p, h->p_pad, 1.0, 1, s));
+    if (h->opt.reg_eps_G != 0.0) CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, 0, p, h->opt.reg_eps_G, 1, s));
+    CIP_TRY(make_q4_tensor_map(&h->mapZ.map, h->Z4, h->p_pad, h->n_pad / 4));
+    CIP_TRY(chol_make_plan(&h->cholS, h->S4, h->p_pad, h->WinvS, h->info + 1));
+  }
+
+  // ---- work vectors
+  for (auto& v : h->nv) CIP_TRY(dev_alloc(h, &v, h->n_pad + 4));
+  for (auto& v : h->mv) CIP_TRY(dev_alloc(h, &v, h->m_pad + 4));
+  for (auto& v : h->pv) CIP_TRY(dev_alloc(h, &v, h->p_pad + 4));
+  h->partial_cap = 4 * 148 * 8 * 128 + 64 * std::max(n, std::max(p, 1));
+  CIP_TRY(dev_alloc(h, &h->partial, h->partial_cap));
+  CIP_TRY(dev_alloc(h, &h->scalar, 8));
+  CIP_CUDA(cudaStreamSynchronize(s));
+  h->st.n = n; h->st.m = m; h->st.p = p; h->st.n_pad = h->n_pad; h->st.m_pad = h->m_pad; h->st.p_pad = h->p_pad;
+  *out = h;
+  return 0;
+}
+
+int cip_destroy(cip_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm) {
+    const NcclApi* api = nccl_api();
+    if (api) api->CommDestroy(h->comm);
+  }
+  void* ptrs[] = {h->At4, h->Atil4, h->Qq4, h->H4, h->Winv, h->G4, h->Z4, h->S4, h->Sbase4, h->WinvS, h->info,
+                  h->d_type, h->d_off, h->d_rowcone, h->d_qlist, h->d_slist, h->F.kind, h->F.a, h->F.b, h->F.D,
+                  h->Fi.kind, h->Fi.a, h->Fi.b, h->Fi.D, h->partial, h->scalar};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto v : h->nv) if (v) cudaFree(v);
+  for (auto v : h->mv) if (v) cudaFree(v);
+  for (auto v : h->pv) if (v) cudaFree(v);
+  for (auto e : h->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int cip_nccl_unique_id(unsigned char id_out[128]) {
+  const NcclApi* api = nccl_api();
+  if (!api) return -1;
+  NcclId id;
+  int r = api->GetUniqueId(&id);
+  if (r != 0) {
+    set_error("ncclGetUniqueId failed: %s", api->GetErrorString(r));
+    return -1;
+  }
+  memcpy(id_out, id.internal, 128);
+  return 0;
+}
+
+int cip_comm_init(cip_handle h, int nranks, int rank, const unsigned char id[128]) {
+  CIP_TRY(check(h));
+  if (nranks <= 1) return 0;
+  const NcclApi* api = nccl_api();
+  if (!api) return -1;
+  NcclId nid;
+  memcpy(nid.internal, id, 128);
+  int r = api->CommInitRank(&h->comm, nranks, nid, rank);
+  if (r != 0) {
+    set_error("ncclCommInitRank failed: %s", api->GetErrorString(r));
+    h->comm = nullptr;
+    return -1;
+  }
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+int cip_set_scaling(cip_handle h, const int* kind, const double* fa, const double* fb, const double* fD,
+                    const double* fR) {
+  CIP_TRY(check(h));
+  return set_scaling_from_user(h, kind, fa, fb, fD, fR);
+}
+
+int cip_form_H(cip_handle h) {
+  CIP_TRY(check(h));
+  CIP_TRY(form_H(h));
+  return 0;
+}
+
+int cip_factor_H(cip_handle h) {
+  CIP_TRY(check(h));
+  CIP_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  return factor_H(h);
+}
+
+int cip_factor(cip_handle h, const int* kind, const double* fa, const double* fb, const double* fD,
+               const double* fR) {
+  CIP_TRY(check(h));
+  CIP_TRY(set_scaling_from_user(h, kind, fa, fb, fD, fR));
+  CIP_TRY(form_H(h));
+  return factor_H(h);
+}
+
+int cip_nt_scaling(cip_handle h, const double* v, const double* s, double* lambda_out) {
+  CIP_TRY(check(h));
+  CIP_TRY(stage_in(h, h->mv[7], v, h->m));
+  CIP_TRY(stage_in(h, h->mv[8], s, h->m));
+  CIP_TRY(cone_nt_scaling(h->cd, h->mv[7], h->mv[8], h->F, h->Fi, h->mv[9], h->stream));
+  h->have_scaling = true;
+  CIP_TRY(stage_out(h, lambda_out, h->mv[9], h->m));
+  return finish(h);
+}
+
+int cip_factor_from_point(cip_handle h, const double* v, const double* s, double* lambda_out) {
+  CIP_TRY(cip_nt_scaling(h, v, s, lambda_out));
+  CIP_TRY(form_H(h));
+  return factor_H(h);
+}
+
+int cip_get_scaling(cip_handle h, int* kind, double* fa, double* fb, double* fD, double* fR) {
+  (void)fR;
+  CIP_TRY(check(h));
+  if (!h->have_scaling) { set_error("no scaling set"); return -1; }
+  if (kind) {
+    CIP_CUDA(cudaMemcpyAsync(kind, h->F.kind, sizeof(int) * h->ncones, cudaMemcpyDefault, h->stream));
+    h->need_sync = true;
+  }
+  CIP_TRY(stage_out(h, fa, h->F.a, h->m));
+  CIP_TRY(stage_out(h, fb, h->F.b, h->m));
+  CIP_TRY(stage_out(h, fD, h->F.D, h->ncones));
+  return finish(h);
+}
+
+int cip_apply(cip_handle h, int op, const double* x, double* y) {
+  CIP_TRY(check(h));
+  if (!h->have_scaling) { set_error("no scaling set"); return -1; }
+  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
+  const Scaling& S = (op == CIP_OP_F || op == CIP_OP_FT) ? h->F : h->Fi;   // R/Q blocks are symmetric
+  CIP_TRY(cone_apply(h->cd, S, h->mv[7], h->mv[8], h->stream));
+  CIP_TRY(stage_out(h, y, h->mv[8], h->m));
+  return finish(h);
+}
+
+int cip_maxstep(cip_handle h, const double* x, const double* d, double d_scale, double* alpha_out) {
+  CIP_TRY(check(h));
+  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
+  if (d) CIP_TRY(stage_in(h, h->mv[8], d, h->m));
+  CIP_TRY(cone_maxstep(h->cd, h->mv[7], d ? h->mv[8] : nullptr, d_scale, nullptr, 0, h->scalar, h->stream));
+  unsigned long long key = 0;
+  CIP_CUDA(cudaMemcpyAsync(&key, h->scalar, 8, cudaMemcpyDeviceToHost, h->stream));
+  CIP_CUDA(cudaStreamSynchronize(h->stream));
+  const unsigned long long u = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+  double r;
+  memcpy(&r, &u, 8);
+  *alpha_out = r;
+  return 0;
+}
+
+int cip_cone_prod(cip_handle h, const double* x, const double* y, double* o) {
+  CIP_TRY(check(h));
+  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
+  CIP_TRY(stage_in(h, h->mv[8], y, h->m));
+  CIP_TRY(cone_prod(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
+  CIP_TRY(stage_out(h, o, h->mv[9], h->m));
+  return finish(h);
+}
+
+int cip_cone_div(cip_handle h, const double* x, const double* y, double* o) {
+  CIP_TRY(check(h));
+  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
+  CIP_TRY(stage_in(h, h->mv[8], y, h->m));
+  CIP_TRY(cone_div(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
+  CIP_TRY(stage_out(h, o, h->mv[9], h->m));
+  return finish(h);
+}
+
+int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv, double* dy, double* dw,
+              double* dv) {
+  CIP_TRY(check(h));
+  if (!h->have_factor) { set_error("cip_solve before cip_factor"); return -1; }
+  cudaStream_t s = h->stream;
+  CIP_CUDA(cudaEventRecord(h->ev[6], s));
+  CIP_TRY(stage_in(h, h->nv[0], ry, h->n));
+  if (h->p) CIP_TRY(stage_in(h, h->pv[0], rw, h->p));
+  CIP_TRY(stage_in(h, h->mv[0], rv, h->m));
+  // t1 = F^-T (F^-T v)                                   (src/kktsolvers.jl:326)
+  CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[0], h->mv[1], s));
+  CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[1], h->mv[2], s));
+  // rhs = y + A' t1                                      (:327)
+  if (h->m) {
+    CIP_TRY(q4_mv_rows(h->nv[1], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->partial, h->partial_cap, s));
+  } else {
+    CIP_TRY(fill_zero(h->nv[1], h->n, s));
+  }
+  CIP_TRY(allreduce(h, h->nv[1], h->n));
+  CIP_TRY(vec_axpby(h->nv[2], 1.0, h->nv[0], 1.0, h->nv[1], h->n, s));
+  // 2x2 solve with H = L L' and the Schur complement on G (:299)
+  CIP_TRY(chol_fwd(h->cholH, h->nv[2], h->nv[3], s));
+  if (h->p) {
+    CIP_TRY(q4_mv_rows(h->pv[1], h->Z4, h->p_pad, h->p, h->n, h->nv[3], h->partial, h->partial_cap, s));
+    CIP_TRY(vec_axpby(h->pv[2], 1.0, h->pv[1], -1.0, h->pv[0], h->p, s));
+    CIP_TRY(chol_fwd(h->cholS, h->pv[2], h->pv[3], s));
+    CIP_TRY(chol_bwd(h->cholS, h->pv[3], h->pv[4], s));
+    CIP_TRY(q4_mv_k(h->nv[4], h->Z4, h->p_pad, h->p, h->n, h->pv[4], s));
+    CIP_TRY(vec_axpby(h->nv[3], 1.0, h->nv[3], -1.0, h->nv[4], h->n, s));
+  }
+  CIP_TRY(chol_bwd(h->cholH, h->nv[3], h->nv[5], s));
+  // dv = t1 - F^-T F^-T (A dy)                           (:328)
+  if (h->m) {
+    CIP_TRY(q4_mv_k(h->mv[3], h->At4, h->n_pad, h->n, h->m, h->nv[5], s));
+    CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[3], h->mv[1], s));
+    CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[1], h->mv[4], s));
+    CIP_TRY(vec_axpby(h->mv[5], 1.0, h->mv[2], -1.0, h->mv[4], h->m, s));
+  }
+  CIP_CUDA(cudaEventRecord(h->ev[7], s));
+  CIP_TRY(stage_out(h, dy, h->nv[5], h->n));
+  if (h->p) CIP_TRY(stage_out(h, dw, h->pv[4], h->p));
+  CIP_TRY(stage_out(h, dv, h->mv[5], h->m));
+  h->st.solves++;
+  return finish(h);
+}
+
+int cip_mul_A(cip_handle h, int trans, const double* x, double* y) {
+  CIP_TRY(check(h));
+  cudaStream_t s = h->stream;
+  if (!trans) {
+    CIP_TRY(stage_in(h, h->nv[6], x, h->n));
+    CIP_TRY(q4_mv_k(h->mv[6], h->At4, h->n_pad, h->n, h->m, h->nv[6], s));
+    CIP_TRY(stage_out(h, y, h->mv[6], h->m));
+  } else {
+    CIP_TRY(stage_in(h, h->mv[6], x, h->m));
+    if (h->m) CIP_TRY(q4_mv_rows(h->nv[6], h->At4, h->n_pad, h->n, h->m, h->mv[6], h->partial, h->partial_cap, s));
+    else CIP_TRY(fill_zero(h->nv[6], h->n, s));
+    CIP_TRY(allreduce(h, h->nv[6], h->n));
+    CIP_TRY(stage_out(h, y, h->nv[6], h->n));
+  }
+  return finish(h);
+}
+
+int cip_mul_G(cip_handle h, int trans, const double* x, double* y) {
+  CIP_TRY(check(h));
+  cudaStream_t s = h->stream;
+  if (h->p == 0) {
+    if (trans) {
+      CIP_TRY(fill_zero(h->nv[6], h->n, s));
+      CIP_TRY(stage_out(h, y, h->nv[6], h->n));
+    }
+    return finish(h);
+  }
+  if (!trans) {
+    CIP_TRY(stage_in(h, h->nv[6], x, h->n));
+    CIP_TRY(q4_mv_rows(h->pv[5], h->G4, h->p_pad, h->p, h->n, h->nv[6], h->partial, h->partial_cap, s));
+    CIP_TRY(stage_out(h, y, h->pv[5], h->p));
+  } else {
+    CIP_TRY(stage_in(h, h->pv[5], x, h->p));
+    CIP_TRY(q4_mv_k(h->nv[6], h->G4, h->p_pad, h->p, h->n, h->pv[5], s));
+    CIP_TRY(stage_out(h, y, h->nv[6], h->n));
+  }
+  return finish(h);
+}
+
+int cip_mul_Q(cip_handle h, const double* x, double* y) {
+  CIP_TRY(check(h));
+  cudaStream_t s = h->stream;
+  CIP_TRY(stage_in(h, h->nv[6], x, h->n));
+  CIP_TRY(q4_mv_rows(h->nv[7], h->Qq4, h->n_pad, h->n, h->n, h->nv[6], h->partial, h->partial_cap, s));
+  CIP_TRY(stage_out(h, y, h->nv[7], h->n));
+  return finish(h);
+}
+
+int cip_stats(cip_handle h, cip_stats_t* out) {
+  CIP_TRY(check(h));
+  float ms = 0;
+  if (h->st.solves > 0 && cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->st.ms_solve = ms;
+  else cudaGetLastError();
+  h->st.device_bytes = h->bytes;
+  h->st.kernel_launches = cip::g_launches;
+  *out = h->st;
+  return 0;
+}
+
+int cip_get_H(cip_handle h, double* out, int ldo) {
+  CIP_TRY(check(h));
+  double* tmp = nullptr;
+  CIP_CUDA(cudaMalloc(&tmp, (size_t)h->n * h->n * 8));
+  CIP_TRY(unpack_rows_q4(tmp, h->n, h->H4, h->n_pad, h->n, h->n, h->stream));
+  CIP_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * 8, tmp, (size_t)h->n * 8, (size_t)h->n * 8, h->n, cudaMemcpyDefault,
+                             h->stream));
+  CIP_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  return 0;
+}
+
+int cip_sync(cip_handle h) {
+  CIP_TRY(check(h));
+  CIP_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void* cip_stream(cip_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int cip_set_stream(cip_handle h, void* stream) {
+  CIP_TRY(check(h));
+  CIP_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = reinterpret_cast<cudaStream_t>(stream);
+  return 0;
+}
+
+int cip_measure_fp64_peaks(int device, double* dmma_tflops, double* dfma_tflops) {
+  if (device >= 0) CIP_CUDA(cudaSetDevice(device));
+  return measure_fp64_peaks(dmma_tflops, dfma_tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// FP64 tensor-core (DMMA.8x8x4) NT tile kernel, TMA + mbarrier pipeline, sm_100a.
+// See gemm_nt.cuh for the contract.
+//
+// CTA = 9 warps: warp 8 is the TMA producer (one elected lane), warps 0..7 are DMMA
+// consumers, each owning a 64 x 32 sub-tile of the 128 x 128 CTA tile (64 FP64
+// accumulators per thread).  A stage is KT = 32 contraction steps: four TMA boxes
+// (X rows 0-63, X rows 64-127, Y rows 0-63, Y rows 64-127), each {256 doubles, 8 quads}
+// = 16 KB, landing in shared memory already in DMMA fragment order, so every operand
+// fragment is one conflict-free 256-byte LDS.64.
+#include "gemm_nt.cuh"
+
+namespace cip {
+
+namespace {
+constexpr int BM = 128, BN = 128;
+constexpr int KT = 32;
+constexpr int KQ = KT / 4;
+constexpr int STAGES = 3;
+constexpr int HALF = 64;
+constexpr int BOX_DOUBLES = HALF * 4 * KQ;       // 2048 doubles
+constexpr int BOX_BYTES = BOX_DOUBLES * 8;       // 16 KB
+constexpr int STAGE_DOUBLES = 4 * BOX_DOUBLES;   // 64 KB
+constexpr int CONSUMER_WARPS = 8;
+constexpr int NUM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+               const GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + STAGES;
+
+  int ti, tj;
+  if (a.lower) {
+    const int t = blockIdx.x;
+    int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    while (r * (r + 1) / 2 > t) --r;
+    ti = r;
+    tj = t - r * (r + 1) / 2;
+  } else {
+    ti = blockIdx.x % a.ntm;
+    tj = blockIdx.x / a.ntm;
+  }
+  const bool same = a.sym && (ti == tj);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmY);
+      const int xr = (a.x_row0 + ti * BM) * 4;
+      const int yr = (a.y_row0 + tj * BN) * 4;
+      const uint32_t bytes = same ? 2u * BOX_BYTES : 4u * BOX_BYTES;
+      for (int kt = 0; kt < a.nk; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        double* st = tiles + (size_t)s * STAGE_DOUBLES;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        tma_load_2d(st, &tmX, &full[s], xr, a.x_kq0 + kt * KQ);
+        tma_load_2d(st + BOX_DOUBLES, &tmX, &full[s], xr + HALF * 4, a.x_kq0 + kt * KQ);
+        if (!same) {
+          tma_load_2d(st + 2 * BOX_DOUBLES, &tmY, &full[s], yr, a.y_kq0 + kt * KQ);
+          tma_load_2d(st + 3 * BOX_DOUBLES, &tmY, &full[s], yr + HALF * 4, a.y_kq0 + kt * KQ);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- DMMA consumers
+  const int g = lane >> 2, t = lane & 3;
+  const int warp_m = warp & 1, warp_n = warp >> 1;
+  double acc[8][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  const int x_off = warp_m * BOX_DOUBLES + g * 4 + t;
+  const int y_off = (same ? 0 : 2 * BOX_DOUBLES) + (warp_n >> 1) * BOX_DOUBLES + ((warp_n & 1) * 32 + g) * 4 + t;
+
+  for (int kt = 0; kt < a.nk; ++kt) {
+    const int s = kt % STAGES;
+    const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+    mbar_wait(&full[s], ph);
+    const double* st = tiles + (size_t)s * STAGE_DOUBLES;
+    const double* xs = st + x_off;
+    const double* ys = st + y_off;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      double av[8], bv[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) av[mi] = xs[(q * HALF + mi * 8) * 4];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bv[ni] = ys[(q * HALF + ni * 8) * 4];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], av[mi], bv[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // -------------------------------------------------------------- epilogue
+  const int row_base = a.c_row0 + ti * BM + warp_m * 64 + g;
+  const int col_base = a.c_col0 + tj * BN + warp_n * 32 + 2 * t;
+  const double alpha = a.alpha;
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) {
+    const int col = col_base + ni * 8;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int row = row_base + mi * 8;
+      const size_t idx = q4_index(row, col, a.ldc);
+      double2 v = make_double2(0.0, 0.0);
+      if (a.Cin) v = *reinterpret_cast<const double2*>(a.Cin + idx);
+      v.x += alpha * acc[mi][ni][0];
+      v.y += alpha * acc[mi][ni][1];
+      *reinterpret_cast<double2*>(a.Cout + idx) = v;
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+bool g_attr_set = false;
+}  // namespace
+
+int gemm_nt_smem_bytes() { return SMEM_BYTES; }
+
+int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long kq_total) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return -1;
+    }
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  if (kq_total < KQ) kq_total = KQ;  // caller guarantees the allocation covers it
+  cuuint64_t gdim[2] = {(cuuint64_t)ld * 4ull, (cuuint64_t)kq_total};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 32ull};
+  cuuint32_t box[2] = {(cuuint32_t)(HALF * 4), (cuuint32_t)KQ};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
+                        estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (ld=%d kq=%lld base=%p)", (int)r, ld, kq_total,
+              (const void*)base);
+    return -1;
+  }
+  return 0;
+}
+
+int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a, cudaStream_t stream) {
+  if (!g_attr_set) {
+    CIP_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    g_attr_set = true;
+  }
+  const long long tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
+  if (tiles <= 0 || a.nk <= 0) return 0;
+  gemm_nt_kernel<<<(unsigned)tiles, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, a);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cip

@@ -1,0 +1,87 @@
+// Host-callable launchers for the bandwidth-bound kernels (layout, mat-vec, cone, Cholesky
+// panel, triangular sweeps).  All take an explicit stream and return 0 / -1.
+#pragma once
+#include "common.cuh"
+#include "gemm_nt.cuh"
+
+namespace cip {
+
+// ---------------------------------------------------------------- layout (layout.cu)
+// dst[q4(r,k)] = (r<R && k<K) ? src[r + k*lds] : 0   for r < Rpad, k < Kpad   (Q, G: rows stay rows)
+int pack_rows_q4(double* dst, int ld, const double* src, int lds, int R, int K, int Rpad, int Kpad,
+                 cudaStream_t s);
+// dst[q4(r0+r,k)] = k<K ? src[k + r*lds] : 0   for r < nc, k < Kpad   (A: columns of A become rows;
+// src is a chunk of nc columns of the column-major A, so uploads can be chunked)
+int pack_trans_q4(double* dst, int ld, int r0, const double* src, int lds, int K, int Kpad, int nc,
+                  cudaStream_t s);
+int unpack_rows_q4(double* dst, int ldd, const double* src, int ld, int R, int K, cudaStream_t s);
+int add_diag_q4(double* X, int ld, int from, int to, double val, int set, cudaStream_t s);
+int set_diag_vec_q4(double* X, int ld, int n, const double* v, cudaStream_t s);
+int fill_zero(double* p, size_t n, cudaStream_t s);
+
+// ---------------------------------------------------------------- mat-vec on Q4 (matvec.cu)
+// out[r] (+)= sum_k X[r,k] v[k]   (thread per row; deterministic two-pass over k splits)
+// v must be readable and finite up to round_up(K,4).
+int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double* v, double* partial,
+               int partial_capacity, cudaStream_t s);
+// out[k] = sum_r X[r,k] u[r]      (warp per k-quad)
+int q4_mv_k(double* out, const double* X, int ld, int R, int K, const double* u, cudaStream_t s);
+
+// ---------------------------------------------------------------- cone kernels (cones.cu)
+struct ConeDesc {
+  int m, ncones;
+  const int* type;      // [ncones] CIP_CONE_*
+  const int* off;       // [ncones+1]
+  const int* row_cone;  // [m] cone index per row
+  const int* qlist;     // [nq] indices of Q cones
+  int nq;
+  const int* slist;     // [ns] indices of S cones
+  int ns;
+  int max_q_dim;
+  int max_s_ord;
+};
+struct Scaling {   // flattened block-diagonal operator: per cone  diag(a) + D * b b'   (kind 1) or diag(a) (kind 0)
+  int* kind;       // [ncones]
+  double* a;       // [m]
+  double* b;       // [m]
+  double* D;       // [ncones]
+};
+
+int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling F, Scaling Fi, double* lambda,
+                    cudaStream_t st);
+int cone_invert_scaling(const ConeDesc& c, Scaling F, Scaling Fi, cudaStream_t st);
+int cone_apply(const ConeDesc& c, Scaling F, const double* x, double* y, cudaStream_t st);
+int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
+int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
+// result (device scalar) = min over cones; d == nullptr -> `nothing` variant
+int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, double* partial,
+                 int npartial, double* result, cudaStream_t st);
+// Atil = F^-T A on the Q4 transposed panel (rows = columns of A, k = rows of A)
+int cone_scale_panel(const ConeDesc& c, Scaling Fi, const double* At4, double* Atil4, int ld, int m_pad,
+                     int ncols, cudaStream_t st);
+
+// ---------------------------------------------------------------- Cholesky (chol.cu)
+struct CholPlan {
+  double* H;        // Q4, ld = n_pad
+  int ld;           // n_pad (multiple of 128)
+  int npanels;
+  double* Winv;     // [npanels][32][128][4]
+  GemmOperand mapH;     // over H
+  GemmOperand mapWinv;  // over Winv viewed as Q4 with ld = 128, kq_total = 32*npanels
+  int* info;        // device int
+};
+int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info);
+int chol_factor(const CholPlan& p, cudaStream_t s);
+// b (length n_pad) is overwritten with work; y receives the solution of L y = b
+int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s);
+// y is overwritten with work; x receives the solution of L' x = y
+int chol_bwd(const CholPlan& p, double* y, double* x, cudaStream_t s);
+
+// small vector helpers (vecops.cu)
+int vec_axpby(double* out, double a, const double* x, double b, const double* y, size_t n, cudaStream_t s);
+int vec_copy(double* out, const double* x, size_t n, cudaStream_t s);
+
+// FP64 pipe microbenchmarks (peaks.cu)
+int measure_fp64_peaks(double* dmma_tflops, double* dfma_tflops);
+
+}  // namespace cip

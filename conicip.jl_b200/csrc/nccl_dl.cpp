@@ -1,0 +1,33 @@
+#include "nccl_dl.h"
+
+#include <dlfcn.h>
+
+namespace cip {
+void set_error(const char* fmt, ...);
+
+const NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.loaded) return &api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("dlopen(libnccl.so.2) failed: %s", dlerror());
+    return nullptr;
+  }
+#define CIP_SYM(field, name)                                       \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name)); \
+  if (!api.field) {                                                \
+    set_error("dlsym(%s) failed", name);                           \
+    return nullptr;                                                \
+  }
+  CIP_SYM(GetUniqueId, "ncclGetUniqueId")
+  CIP_SYM(CommInitRank, "ncclCommInitRank")
+  CIP_SYM(AllReduce, "ncclAllReduce")
+  CIP_SYM(CommDestroy, "ncclCommDestroy")
+  CIP_SYM(GetErrorString, "ncclGetErrorString")
+#undef CIP_SYM
+  api.loaded = true;
+  return &api;
+}
+
+}  // namespace cip

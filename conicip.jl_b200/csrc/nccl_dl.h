@@ -1,0 +1,30 @@
+// Minimal NCCL binding resolved with dlopen("libnccl.so.2") at run time, so the library
+// neither links a second NCCL next to the one the host process (PyTorch, Julia) already
+// loaded nor needs NCCL at all for single-GPU use.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace cip {
+
+struct NcclId {
+  char internal[128];
+};
+
+struct NcclApi {
+  bool loaded = false;
+  int (*GetUniqueId)(NcclId* id) = nullptr;
+  int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank) = nullptr;
+  int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm,
+                   cudaStream_t stream) = nullptr;
+  int (*CommDestroy)(void* comm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+// returns nullptr (and sets the error string) if libnccl cannot be loaded
+const NcclApi* nccl_api();
+
+constexpr int kNcclFloat64 = 8;
+constexpr int kNcclSum = 0;
+
+}  // namespace cip

@@ -1,0 +1,298 @@
+"""`Engine`: thin object wrapper over one `cip_handle` (include/conicip_b200.h).
+
+Vectors may be NumPy arrays (host; results come back as NumPy) or CUDA
+`torch.Tensor`s (device; results stay on the device, no PCIe traffic).  PyTorch is
+only used to own device memory -- every computation happens in libconicip_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import CONE_CODE, Options, Stats, check, lib
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr")
+
+
+def _colmajor(M):
+    """Dense column-major float64 (Julia layout) from dense / scipy.sparse / torch input."""
+    if M is None:
+        return None
+    if _is_torch(M):
+        return M
+    if sp.issparse(M):
+        M = M.toarray()
+    return np.asfortranarray(M, dtype=np.float64)
+
+
+class Engine:
+    """LEVEL-1 object: `kktsolver(Q, A, G, cone_dims)` (src/ConicIP.jl:667)."""
+
+    def __init__(self, Q, A, G, cone_dims, *, reg_delta=0.0, reg_eps_G=0.0, device=-1,
+                 use_torch_stream=True):
+        L = lib()
+        self.cone_dims = [(t, int(k)) for t, k in cone_dims]
+        self.cone_type = np.array([CONE_CODE[t] for t, _ in self.cone_dims], dtype=np.int32)
+        self.cone_dim = np.array([k for _, k in self.cone_dims], dtype=np.int32)
+        self.cone_off = np.concatenate([[0], np.cumsum(self.cone_dim)]).astype(np.int64)
+        m_c = int(self.cone_off[-1])
+
+        opts = Options()
+        opts.struct_size = C.sizeof(Options)
+        opts.device = device
+        opts.reg_delta = reg_delta
+        opts.reg_eps_G = reg_eps_G
+        opts.q_kind = 0
+
+        # ---- Q: dense, sparse, diagonal vector ("Id(n)", src/ConicIP.jl:18) or None (zero)
+        if Q is None:
+            opts.q_kind = 2
+            q_ptr, ldq, n = None, 0, None
+            self._Q = None
+        elif not _is_torch(Q) and sp.issparse(Q) and (Q - sp.diags(Q.diagonal())).nnz == 0:
+            self._Q = np.ascontiguousarray(Q.diagonal(), dtype=np.float64)
+            opts.q_kind = 1
+            q_ptr, ldq, n = self._Q.ctypes.data, 1, Q.shape[0]
+        else:
+            self._Q = _colmajor(Q)
+            n = self._Q.shape[0]
+            if _is_torch(self._Q):
+                # torch is row-major; Q is symmetric so the transpose is the same matrix
+                q_ptr, ldq = self._Q.data_ptr(), self._Q.stride(0)
+            else:
+                q_ptr, ldq = self._Q.ctypes.data, n
+
+        # ---- A: (m x n).  torch input must already be column-major: a (n x m) row-major tensor
+        #      passed as `A_colmajor_t` semantics -> we accept A.t() views (stride(0) == 1).
+        A = _colmajor(A)
+        if _is_torch(A):
+            m, nA = A.shape
+            if m > 1 and A.stride(0) != 1:
+                raise ValueError("device A must be column-major: pass X.t() of a contiguous (n, m) tensor")
+            a_ptr, lda = A.data_ptr(), (A.stride(1) if nA > 1 else m)
+        else:
+            m, nA = A.shape
+            a_ptr, lda = (A.ctypes.data if m else None), max(m, 1)
+        if n is None:
+            n = nA
+        if nA != n:
+            raise ValueError("Inconsistency in inequalities/objective")
+        if m_c != m:
+            raise ValueError("cone_dims do not cover the rows of A")
+
+        if G is None:
+            p, g_ptr, ldg = 0, None, 1
+            self._G = None
+        else:
+            self._G = _colmajor(G)
+            p = self._G.shape[0]
+            if self._G.shape[1] != n and p > 0:
+                raise ValueError("Inconsistency in equalities/objective")
+            if _is_torch(self._G):
+                g_ptr, ldg = self._G.data_ptr(), self._G.stride(1)
+            else:
+                g_ptr, ldg = (self._G.ctypes.data if p else None), max(p, 1)
+
+        self.n, self.m, self.p = int(n), int(m), int(p)
+        self._h = C.c_void_p()
+        rc = L.cip_create(C.byref(self._h), self.n, self.m, self.p, q_ptr, ldq, a_ptr, lda, g_ptr, ldg,
+                          len(self.cone_dims), self.cone_type.ctypes.data, self.cone_dim.ctypes.data,
+                          C.byref(opts))
+        if rc != 0:
+            raise _lib.CipError(rc, _lib.last_error())
+        self._torch = None
+        self._use_torch_stream = use_torch_stream
+        self.last_factor_status = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().cip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _bind_stream(self):
+        if self._torch is None:
+            import torch
+            self._torch = torch
+        if self._use_torch_stream:
+            check(lib().cip_set_stream(self._h, self._torch.cuda.current_stream().cuda_stream))
+
+    def _ptr(self, x, length):
+        if x is None:
+            return None
+        if _is_torch(x):
+            if not x.is_cuda or x.dtype != self._dtype() or not x.is_contiguous() or x.numel() != length:
+                raise ValueError("device vectors must be contiguous CUDA float64 of the right length")
+            return x.data_ptr()
+        if x.dtype != np.float64 or not x.flags.c_contiguous or x.size != length:
+            raise ValueError("host vectors must be contiguous float64 of the right length")
+        return x.ctypes.data
+
+    def _dtype(self):
+        return self._torch.float64
+
+    def _prep(self, *xs):
+        """Normalise inputs; decide whether results live on the device."""
+        dev = any(_is_torch(x) for x in xs if x is not None)
+        if dev:
+            self._bind_stream()
+            out = [x if (x is None or _is_torch(x)) else self._torch.as_tensor(np.asarray(x, dtype=np.float64)).cuda()
+                   for x in xs]
+        else:
+            out = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in xs]
+        return dev, out
+
+    def _new(self, dev, length):
+        if dev:
+            return self._torch.empty(length, dtype=self._torch.float64, device="cuda")
+        return np.empty(length, dtype=np.float64)
+
+    # ------------------------------------------------------------------ LEVEL 2
+    def factor(self, F):
+        """`solve3x3gen(F, F^-T)` with a host `Block` (flattened) -- src/ConicIP.jl:682."""
+        kind, fa, fb, fD, fR = F.flatten()
+        if len(kind) != len(self.cone_dims) or len(fa) != self.m:
+            raise ValueError("F does not match cone_dims")
+        rc = lib().cip_factor(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data,
+                              None if fR is None else fR.ctypes.data)
+        self.last_factor_status = check(rc)
+        return rc
+
+    def factor_resident(self):
+        """Form + factor with the scaling already resident (after nt_scaling / set_scaling)."""
+        check(lib().cip_form_H(self._h))
+        rc = lib().cip_factor_H(self._h)
+        self.last_factor_status = check(rc)
+        return rc
+
+    def form_H(self):
+        check(lib().cip_form_H(self._h))
+
+    def factor_H(self):
+        rc = lib().cip_factor_H(self._h)
+        self.last_factor_status = check(rc)
+        return rc
+
+    def factor_from_point(self, v, s):
+        dev, (v, s) = self._prep(v, s)
+        lam = self._new(dev, self.m)
+        rc = lib().cip_factor_from_point(self._h, self._ptr(v, self.m), self._ptr(s, self.m), self._ptr(lam, self.m))
+        self.last_factor_status = check(rc)
+        return lam
+
+    def set_scaling(self, F):
+        kind, fa, fb, fD, fR = F.flatten()
+        check(lib().cip_set_scaling(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data,
+                                    None if fR is None else fR.ctypes.data))
+
+    def get_scaling(self):
+        nc = len(self.cone_dims)
+        kind = np.zeros(nc, dtype=np.int32)
+        fa, fb, fD = np.zeros(self.m), np.zeros(self.m), np.zeros(nc)
+        check(lib().cip_get_scaling(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data, None))
+        return kind, fa, fb, fD
+
+    # ------------------------------------------------------------------ LEVEL 3
+    def solve(self, ry, rw, rv):
+        """`solve3x3(y, w, v) -> (a, b, c)` -- src/kktsolvers.jl:324-332."""
+        if rw is None or len(rw) == 0:
+            rw = None
+        dev, (ry, rw, rv) = self._prep(ry, rw, rv)
+        dy, dv = self._new(dev, self.n), self._new(dev, self.m)
+        dw = self._new(dev, self.p)
+        check(lib().cip_solve(self._h, self._ptr(ry, self.n), self._ptr(rw, self.p) if self.p else None,
+                              self._ptr(rv, self.m), self._ptr(dy, self.n),
+                              self._ptr(dw, self.p) if self.p else None, self._ptr(dv, self.m)))
+        return dy, dw, dv
+
+    # ------------------------------------------------------------------ cone kernels
+    def nt_scaling(self, v, s):
+        dev, (v, s) = self._prep(v, s)
+        lam = self._new(dev, self.m)
+        check(lib().cip_nt_scaling(self._h, self._ptr(v, self.m), self._ptr(s, self.m), self._ptr(lam, self.m)))
+        return lam
+
+    def apply(self, op, x):
+        dev, (x,) = self._prep(x)
+        y = self._new(dev, self.m)
+        check(lib().cip_apply(self._h, op, self._ptr(x, self.m), self._ptr(y, self.m)))
+        return y
+
+    def maxstep(self, x, d=None, d_scale=1.0):
+        dev, (x, d) = self._prep(x, d)
+        a = C.c_double()
+        check(lib().cip_maxstep(self._h, self._ptr(x, self.m), self._ptr(d, self.m), float(d_scale), C.byref(a)))
+        return a.value
+
+    def cone_prod(self, x, y):
+        dev, (x, y) = self._prep(x, y)
+        o = self._new(dev, self.m)
+        check(lib().cip_cone_prod(self._h, self._ptr(x, self.m), self._ptr(y, self.m), self._ptr(o, self.m)))
+        return o
+
+    def cone_div(self, x, y):
+        dev, (x, y) = self._prep(x, y)
+        o = self._new(dev, self.m)
+        check(lib().cip_cone_div(self._h, self._ptr(x, self.m), self._ptr(y, self.m), self._ptr(o, self.m)))
+        return o
+
+    # ------------------------------------------------------------------ resident operators
+    def mul_A(self, x, trans=False):
+        dev, (x,) = self._prep(x)
+        nin, nout = (self.m, self.n) if trans else (self.n, self.m)
+        y = self._new(dev, nout)
+        check(lib().cip_mul_A(self._h, int(trans), self._ptr(x, nin), self._ptr(y, nout)))
+        return y
+
+    def mul_G(self, x, trans=False):
+        dev, (x,) = self._prep(x)
+        nin, nout = (self.p, self.n) if trans else (self.n, self.p)
+        y = self._new(dev, nout)
+        if nout == 0:
+            return y
+        check(lib().cip_mul_G(self._h, int(trans), self._ptr(x, nin) if nin else None, self._ptr(y, nout)))
+        return y
+
+    def mul_Q(self, x):
+        dev, (x,) = self._prep(x)
+        y = self._new(dev, self.n)
+        check(lib().cip_mul_Q(self._h, self._ptr(x, self.n), self._ptr(y, self.n)))
+        return y
+
+    # ------------------------------------------------------------------ multi-GPU / misc
+    def comm_init(self, nranks, rank, unique_id):
+        check(lib().cip_comm_init(self._h, nranks, rank, unique_id))
+
+    def stats(self):
+        st = Stats()
+        check(lib().cip_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    def get_H(self):
+        out = np.zeros((self.n, self.n), order="F")
+        check(lib().cip_get_H(self._h, out.ctypes.data, self.n))
+        return out
+
+    def sync(self):
+        check(lib().cip_sync(self._h))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().cip_nccl_unique_id(buf))
+    return buf.raw
+
+
+def measure_fp64_peaks(device=-1):
+    a, b = C.c_double(), C.c_double()
+    check(lib().cip_measure_fp64_peaks(device, C.byref(a), C.byref(b)))
+    return {"dmma_tflops": a.value, "dfma_tflops": b.value}

@@ -1,0 +1,132 @@
+"""End-to-end parity of the B200 path behind the reference's interface
+(`conicIP(...; kktsolver=kktsolver_b200)`) against the oracle, the committed golden fixture and
+the reference's own recorded goldens.  Gates from BASELINE.json: iteration count within +-1,
+final y,v,w within 1e-6 relative, prFeas/duFeas/muFeas below the same tolerance."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conicip_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def run_b200(prob, **kw):
+    import conicip_b200 as cb
+    p = prob["G"].shape[0]
+    opts = dict(optTol=prob.get("optTol", 1e-7))
+    opts.update(kw)
+    return cb.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"],
+                      prob["G"] if p else None, prob["d"] if p else None, **opts)
+
+
+def run_oracle(prob, solver=None, **kw):
+    opts = dict(optTol=prob.get("optTol", 1e-7))
+    opts.update(kw)
+    return O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"],
+                     kktsolver=solver or O.pivot(O.kktsolver_2x2), **opts)
+
+
+def assert_parity(s, so, tol):
+    assert s.status == so.status
+    assert abs(s.Iter - so.Iter) <= 1
+    assert rel(s.y, so.y) < RTOL and rel(s.v, so.v) < RTOL
+    if len(so.w):
+        assert rel(s.w, so.w) < RTOL
+    if s.status == "Optimal":
+        assert max(s.prFeas, s.duFeas, s.muFeas) < tol
+
+
+# reference goldens: test/runtests.jl:157-162, :197-202, :235-240
+@pytest.mark.parametrize("gen,it,mu", [(P.sphere, 5, 2.866608128093695e-7), (P.combined, 10, 4.663886012743681e-7)])
+def test_reference_mu_goldens(gen, it, mu):
+    s = run_b200(gen(), DTB=0.01, maxRefinementSteps=3)
+    assert s.status == "Optimal" and abs(s.Iter - it) <= 1
+    mu_at = dict((t[0], t[1]) for t in s.trace)[it]
+    assert abs(mu_at - mu) <= 1e-7 * mu
+
+
+def test_reference_simplex_golden():
+    s = run_b200(P.simplex(), optTol=1e-8)
+    assert s.status == "Optimal" and s.Iter == 11
+    assert abs(s.Mu - 2.7686402945528533e-9) <= 1e-7 * 2.7686402945528533e-9
+    y = np.zeros(10); y[9] = 1
+    assert np.linalg.norm(s.y - y) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["sphere", "combined", "simplex", "soc_direct", "mixed"])
+def test_committed_golden_fixture(name):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_small.json")))["solves"][name]
+    s = run_b200(getattr(P, name)(), optTol=g["optTol"])
+    assert s.status == g["status"] and abs(s.Iter - g["Iter"]) <= 1
+    assert rel(s.y, g["y"]) < RTOL and rel(s.v, g["v"]) < RTOL
+    if len(g["w"]):
+        assert rel(s.w, g["w"]) < RTOL
+    mu = [t[1] for t in s.trace]
+    k = min(len(mu), len(g["mu_trace"]))
+    assert np.allclose(mu[:k], g["mu_trace"][:k], rtol=1e-5)        # same trajectory, not just same end point
+
+
+def test_box_qp_custom_kktsolver_problem():
+    """runtests.jl:90-131 at its full size n=1000 (the reference's own plugin-boundary demo)."""
+    prob = P.box_qp(1000)
+    s = run_b200(prob, DTB=0.01, maxRefinementSteps=3)
+    so = run_oracle(prob, DTB=0.01, maxRefinementSteps=3)
+    assert_parity(s, so, 1e-7)
+    c = np.arange(1.0, 1001)
+    assert np.linalg.norm(s.y - np.clip(c, -1, 1)) / 1000 < 1e-3
+
+
+def test_config1_readme_qp():
+    """C1: README nonnegative QP n=1000 (BASELINE configs[0]) -- full solve vs the oracle."""
+    prob = P.config1()
+    s = run_b200(prob)
+    so = run_oracle(prob)
+    assert_parity(s, so, 1e-8)
+
+
+def test_config3_socp_reduced():
+    """C3 shape at a size the oracle finishes in seconds: 64 Q cones of dim 33, p = 32."""
+    prob = P.config3(n=512, ncones=64, k=33, p=32, seed=3)
+    s = run_b200(prob)
+    so = run_oracle(prob, O.kktsolver_chol)
+    assert_parity(s, so, 1e-8)
+
+
+def test_statuses_abandoned_infeasible_unbounded():
+    assert run_b200(P.simplex(), maxIters=2).status == "Abandoned"         # runtests.jl:246-269
+    assert run_b200(P.infeasible()).status == "Infeasible"                  # runtests.jl:441-460
+    s = run_b200(P.unbounded())                                             # runtests.jl:487-505
+    assert s.status == "Unbounded" and np.all(np.isnan(s.v))
+
+
+def test_bad_input_throws():
+    import conicip_b200 as cb
+    n = 10
+    with pytest.raises(Exception):                                          # runtests.jl:507-523
+        cb.conicIP(np.zeros((n, n)), np.arange(1.0, n + 1), np.eye(n + 2), np.zeros(n), [("R", n)])
+
+
+def test_kktsolver_three_level_protocol():
+    """The closure protocol of docs/src/guides/kkt_solvers.md:84-109 used directly."""
+    import conicip_b200 as cb
+    prob = P.mixed()
+    cd = prob["cone_dims"]
+    solve3x3gen = cb.kktsolver_b200(prob["Q"], prob["A"], prob["G"], cd)                   # LEVEL 1
+    F = cb.Block([cb.Diagonal(np.full(k, 2.0)) for _, k in cd])
+    solve3x3 = solve3x3gen(F, None)                                                         # LEVEL 2
+    rng = np.random.default_rng(0)
+    x, y, z = rng.standard_normal(96), rng.standard_normal(5), rng.standard_normal(prob["A"].shape[0])
+    a, b, c = solve3x3(x, y, z)                                                             # LEVEL 3
+    Q, A, G = prob["Q"], prob["A"], prob["G"]
+    assert np.linalg.norm(Q @ a + G.T @ b - A.T @ c - x) < 1e-10 * np.linalg.norm(x) * 10
+    assert np.linalg.norm(G @ a - y) < 1e-10
+    assert np.linalg.norm(A @ a + 4.0 * c - z) < 1e-10 * np.linalg.norm(z) * 10

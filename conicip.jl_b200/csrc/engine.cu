@@ -474,6 +474,8 @@ int cip_destroy(cip_handle h) {
   for (auto v : h->nv) if (v) cudaFree(v);
   for (auto v : h->mv) if (v) cudaFree(v);
   for (auto v : h->pv) if (v) cudaFree(v);
+  chol_free_plan(&h->cholH);
+  chol_free_plan(&h->cholS);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->own_stream);
   delete h;

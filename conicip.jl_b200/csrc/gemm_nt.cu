@@ -21,6 +21,7 @@ constexpr int BOX_DOUBLES = HALF * 4 * KQ;       // 2048 doubles
 constexpr int BOX_BYTES = BOX_DOUBLES * 8;       // 16 KB
 constexpr int STAGE_DOUBLES = 4 * BOX_DOUBLES;   // 64 KB
 constexpr int CONSUMER_WARPS = 8;
+constexpr int BAND = 12;
 constexpr int NUM_THREADS = (CONSUMER_WARPS + 1) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
 
@@ -34,12 +35,28 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   int ti, tj;
   if (a.lower) {
+    // Band rasterisation of the lower-triangular tile grid: bands of BAND tile rows, column-major
+    // inside a band, so the ~148 concurrently resident CTAs cover ~BAND rows x ~148/BAND columns and
+    // share their X / Y panels in L2 (instead of one long row of tiles with 148 distinct Y panels).
     const int t = blockIdx.x;
-    int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-    while ((r + 1) * (r + 2) / 2 <= t) ++r;
-    while (r * (r + 1) / 2 > t) --r;
-    ti = r;
-    tj = t - r * (r + 1) / 2;
+    int b = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f) / BAND;
+    auto before = [](int bb) { const long long R = (long long)bb * BAND; return R * (R + 1) / 2; };
+    while (before(b + 1) <= t) ++b;
+    while (before(b) > t) --b;
+    const int r0 = b * BAND;
+    const int h = (a.ntm - r0 < BAND) ? a.ntm - r0 : BAND;
+    int local = t - (int)before(b);
+    const int full = (r0 + 1) * h;
+    if (local < full) {
+      tj = local / h;
+      ti = r0 + local % h;
+    } else {
+      local -= full;
+      int u = 0, cnt = h - 1;
+      while (local >= cnt) { local -= cnt; ++u; --cnt; }
+      tj = r0 + 1 + u;
+      ti = tj + local;
+    }
   } else {
     ti = blockIdx.x % a.ntm;
     tj = blockIdx.x / a.ntm;

@@ -69,8 +69,13 @@ struct CholPlan {
   GemmOperand mapH;     // over H
   GemmOperand mapWinv;  // over Winv viewed as Q4 with ld = 128, kq_total = 32*npanels
   int* info;        // device int
+  // look-ahead: panel factorisation / TRSM / next-column update run on a high-priority stream
+  // while the bulk trailing update of the previous panel runs on the caller's stream
+  cudaStream_t sc = nullptr;
+  cudaEvent_t evT[2] = {}, evR[2] = {}, evS = nullptr;
 };
 int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info);
+void chol_free_plan(CholPlan* p);
 int chol_factor(const CholPlan& p, cudaStream_t s);
 // b (length n_pad) is overwritten with work; y receives the solution of L y = b
 int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s);

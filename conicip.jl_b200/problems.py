@@ -146,7 +146,8 @@ def mixed(n=96, mr=80, ncones=6, k=9, p=5, seed=7):
     d = G @ y0
     Q = _lowrank_q(rng, n, 8)
     c = rng.standard_normal(n)
-    return _prob("mixed", Q, c, A, b, [("R", mr)] + [("Q", k)] * ncones, G, d, optTol=1e-8)
+    cones = ([("R", mr)] if mr > 0 else []) + [("Q", k)] * ncones
+    return _prob("mixed", Q, c, A, b, cones, G, d, optTol=1e-8)
 
 
 def config4_device(n=16384, m=262144, seed=4, rank=0, nranks=1, scale_rows=None):

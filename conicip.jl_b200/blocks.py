@@ -98,13 +98,17 @@ class DeviceBlock:
 
     def to_host(self):
         """Materialise as a host `Block` (what a Julia caller would see)."""
-        kind, fa, fb, fD = self.engine.get_scaling()
+        kind, fa, fb, fD, Rs = self.engine.get_scaling(with_R=True)
         off = self.engine.cone_off
-        blocks = []
+        blocks, si = [], 0
         for i in range(len(kind)):
             lo, hi = off[i], off[i + 1]
+            is_s = self.engine.cone_dims[i][0] == "S"
             if kind[i] == BLK_DIAG:
                 blocks.append(Diagonal(fa[lo:hi]))
-            else:
+            elif kind[i] == BLK_WOODBURY:
                 blocks.append(SymWoodbury(fa[lo:hi], fb[lo:hi], fD[i]))
+            else:
+                blocks.append(VecCongurance(Rs[si]))
+            si += is_s
         return Block(blocks)

@@ -49,7 +49,9 @@ __device__ __forceinline__ unsigned long long dkey(double x) {
 __global__ void nt_r_kernel(ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
                             Scaling Fi, double* __restrict__ lambda) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
-    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+    const int ty = c.type[c.row_cone[i]];
+    if (ty == CIP_CONE_S) { F.a[i] = 0.0; F.b[i] = 0.0; Fi.a[i] = 0.0; Fi.b[i] = 0.0; }
+    if (ty != CIP_CONE_R) continue;
     const double f = sqrt(s[i] / v[i]);          // Diagonal(sqrt.(yI./xI)), src/ConicIP.jl:598
     F.a[i] = f;
     F.b[i] = 0.0;
@@ -118,9 +120,14 @@ __global__ void nt_q_kernel(ConeDesc c, const double* __restrict__ v, const doub
 // generic inverse of a flattened scaling (used by cip_factor / cip_set_scaling)
 __global__ void inv_diag_kernel(ConeDesc c, Scaling F, Scaling Fi) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
+    const int kd = F.kind[c.row_cone[i]];
+    if (kd == CIP_BLK_VECCONG) {          // handled by the S-cone kernels; keep the flat part inert
+      F.a[i] = 0.0; F.b[i] = 0.0; Fi.a[i] = 0.0; Fi.b[i] = 0.0;
+      continue;
+    }
     const double ia = 1.0 / F.a[i];
     Fi.a[i] = ia;
-    Fi.b[i] = (F.kind[c.row_cone[i]] == CIP_BLK_WOODBURY) ? ia * F.b[i] : 0.0;
+    Fi.b[i] = (kd == CIP_BLK_WOODBURY) ? ia * F.b[i] : 0.0;
   }
 }
 __global__ void inv_wood_kernel(ConeDesc c, Scaling F, Scaling Fi) {
@@ -313,17 +320,14 @@ inline int nblocks(int n, int per) {
   } while (0)
 
 int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling F, Scaling Fi, double* lambda,
-                    cudaStream_t st) {
-  if (c.ns > 0) {
-    set_error("S cones: NT scaling on device not available in this build");
-    return -2;
-  }
+                    int* info, cudaStream_t st) {
   if (c.m == 0) return 0;
   nt_kind_kernel<<<(c.ncones + 255) / 256, 256, 0, st>>>(c, F, Fi);
   CIP_CHECK_LAUNCH();
   nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(nt_q_kernel, c, v, s, F, Fi, lambda);
+  CIP_TRY(sdp_nt_scaling(c, F, Fi, v, s, lambda, info, st));
   return 0;
 }
 
@@ -333,42 +337,47 @@ int cone_invert_scaling(const ConeDesc& c, Scaling F, Scaling Fi, cudaStream_t s
   CIP_CHECK_LAUNCH();
   inv_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, F, Fi);
   CIP_CHECK_LAUNCH();
+  CIP_TRY(sdp_invert(c, F, st));
   return 0;
 }
 
-int cone_apply(const ConeDesc& c, Scaling F, const double* x, double* y, cudaStream_t st) {
+int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, const double* x, double* y,
+               cudaStream_t st) {
   if (c.m == 0) return 0;
-  apply_diag_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c.m, F.a, x, y);
+  const bool inv = (op == CIP_OP_FINVT || op == CIP_OP_FINV);
+  const Scaling& S = inv ? Fi : F;           // R / Q blocks are symmetric: F' = F
+  apply_diag_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c.m, S.a, x, y);
   CIP_CHECK_LAUNCH();
   if (c.nq + c.ns > 0) {   // only non-R cones can carry a Woodbury block
-    apply_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, F, x, y);
+    apply_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, S, x, y);
     CIP_CHECK_LAUNCH();
   }
+  // VecCongurance blocks: F -> R, F' -> R', inv(F) -> inv(R), inv(F)' -> inv(R)'
+  CIP_TRY(sdp_apply(c, F, inv ? 1 : 0, (op == CIP_OP_FT || op == CIP_OP_FINVT) ? 1 : 0, x, y, st));
   return 0;
 }
 
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
-  if (c.ns > 0) { set_error("S cones: cone_prod not available in this build"); return -2; }
   if (c.m == 0) return 0;
   prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(prod_q_kernel, c, x, y, o);
+  CIP_TRY(sdp_prod_div(c, x, y, o, 0, st));
   return 0;
 }
 
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
-  if (c.ns > 0) { set_error("S cones: cone_div not available in this build"); return -2; }
   if (c.m == 0) return 0;
   prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(div_q_kernel, c, x, y, o);
+  CIP_TRY(sdp_prod_div(c, x, y, o, 1, st));
   return 0;
 }
 
 int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, double* partial,
                  int npartial, double* result, cudaStream_t st) {
   (void)partial; (void)npartial;
-  if (c.ns > 0) { set_error("S cones: maxstep not available in this build"); return -2; }
   unsigned long long* key = reinterpret_cast<unsigned long long*>(result);
   maxstep_init_kernel<<<1, 1, 0, st>>>(key);
   CIP_CHECK_LAUNCH();
@@ -376,6 +385,7 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
   maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(maxstep_q_kernel, c, x, d, d_scale, key);
+  CIP_TRY(sdp_maxstep(c, x, d, d_scale, key, st));
   return 0;
 }
 
@@ -390,6 +400,7 @@ int cone_scale_panel(const ConeDesc& c, Scaling Fi, const double* At4, double* A
     scale_panel_wood_kernel<<<g2, 128, 0, st>>>(c, Fi, At4, Atil4, ld, ncols);
     CIP_CHECK_LAUNCH();
   }
+  CIP_TRY(sdp_scale_panel(c, Fi, At4, Atil4, ld, ncols, st));
   return 0;
 }
 

@@ -9,6 +9,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -52,6 +54,9 @@ struct cip_engine {
   // cones
   std::vector<int> h_type, h_off;
   int *d_type = nullptr, *d_off = nullptr, *d_rowcone = nullptr, *d_qlist = nullptr, *d_slist = nullptr;
+  int *d_sord = nullptr, *d_roff = nullptr;
+  std::vector<int> h_slist, h_sord, h_roff;
+  size_t r_total = 0;
   ConeDesc cd{};
   Scaling F{}, Fi{};
   bool have_scaling = false, have_factor = false;
@@ -140,7 +145,6 @@ int allreduce(cip_engine* h, double* buf, size_t count) {
 
 int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, const double* fb, const double* fD,
                           const double* fR) {
-  (void)fR;
   if (!kind || !fa) {
     set_error("cip_factor/cip_set_scaling: kind and fa are required");
     return -1;
@@ -151,13 +155,15 @@ int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, cons
   } else {
     memcpy(hk.data(), kind, sizeof(int) * h->ncones);
   }
-  bool any_w = false;
+  bool any_w = false, any_v = false;
   for (int i = 0; i < h->ncones; ++i) {
     if (hk[i] == CIP_BLK_VECCONG) {
-      set_error("VecCongurance (S cone) scaling blocks are not available in this build");
-      return -2;
-    }
-    if (hk[i] != CIP_BLK_DIAG && hk[i] != CIP_BLK_WOODBURY) {
+      if (h->h_type[i] != CIP_CONE_S) {
+        set_error("VecCongurance block on cone %d, which is not an S cone", i);
+        return -1;
+      }
+      any_v = true;
+    } else if (hk[i] != CIP_BLK_DIAG && hk[i] != CIP_BLK_WOODBURY) {
       set_error("unknown scaling block kind %d for cone %d", hk[i], i);
       return -1;
     }
@@ -176,6 +182,19 @@ int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, cons
   } else {
     CIP_TRY(fill_zero(h->F.b, h->m, h->stream));
     CIP_TRY(fill_zero(h->F.D, h->ncones, h->stream));
+  }
+  if (any_v) {
+    if (!fR) {
+      set_error("VecCongurance blocks need fR");
+      return -1;
+    }
+    size_t src = 0;                       // fR is concatenated over the VECCONG blocks in cone order
+    for (size_t si = 0; si < h->h_slist.size(); ++si) {
+      if (hk[h->h_slist[si]] != CIP_BLK_VECCONG) continue;
+      const size_t kk = (size_t)h->h_sord[si] * h->h_sord[si];
+      CIP_CUDA(cudaMemcpyAsync(h->F.R + h->h_roff[si], fR + src, kk * sizeof(double), cudaMemcpyDefault, h->stream));
+      src += kk;
+    }
   }
   CIP_TRY(cone_invert_scaling(h->cd, h->F, h->Fi, h->stream));
   h->have_scaling = true;
@@ -322,7 +341,22 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
     if (h->h_off[i + 1] > m) break;
     for (int r = h->h_off[i]; r < h->h_off[i + 1]; ++r) rowcone[r] = i;
     if (cone_type[i] == CIP_CONE_Q) { qlist.push_back(i); maxq = std::max(maxq, cone_dim[i]); }
-    else if (cone_type[i] == CIP_CONE_S) { slist.push_back(i); maxs = std::max(maxs, cone_dim[i]); }
+    else if (cone_type[i] == CIP_CONE_S) {
+      const int k = (int)((sqrt(1.0 + 8.0 * cone_dim[i]) - 1.0) / 2.0 + 0.5);
+      if (k * (k + 1) / 2 != cone_dim[i]) {
+        set_error("S cone %d: dimension %d is not k(k+1)/2", i, cone_dim[i]);
+        return -1;
+      }
+      if (k > sdp_max_order()) {
+        set_error("S cone %d: order %d exceeds the supported maximum %d", i, k, sdp_max_order());
+        return -2;
+      }
+      slist.push_back(i);
+      h->h_sord.push_back(k);
+      h->h_roff.push_back((int)h->r_total);
+      h->r_total += (size_t)k * k;
+      maxs = std::max(maxs, k);
+    }
     else if (cone_type[i] != CIP_CONE_R) {
       set_error("unknown cone type %d", cone_type[i]);
       return -1;
@@ -337,22 +371,33 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
   CIP_TRY(dev_alloc(h, &h->d_rowcone, m));
   CIP_TRY(dev_alloc(h, &h->d_qlist, qlist.size()));
   CIP_TRY(dev_alloc(h, &h->d_slist, slist.size()));
+  CIP_TRY(dev_alloc(h, &h->d_sord, slist.size()));
+  CIP_TRY(dev_alloc(h, &h->d_roff, slist.size()));
+  h->h_slist = slist;
   if (ncones) CIP_CUDA(cudaMemcpy(h->d_type, h->h_type.data(), sizeof(int) * ncones, cudaMemcpyHostToDevice));
   CIP_CUDA(cudaMemcpy(h->d_off, h->h_off.data(), sizeof(int) * (ncones + 1), cudaMemcpyHostToDevice));
   if (m) CIP_CUDA(cudaMemcpy(h->d_rowcone, rowcone.data(), sizeof(int) * m, cudaMemcpyHostToDevice));
   if (!qlist.empty())
     CIP_CUDA(cudaMemcpy(h->d_qlist, qlist.data(), sizeof(int) * qlist.size(), cudaMemcpyHostToDevice));
-  if (!slist.empty())
+  if (!slist.empty()) {
     CIP_CUDA(cudaMemcpy(h->d_slist, slist.data(), sizeof(int) * slist.size(), cudaMemcpyHostToDevice));
+    CIP_CUDA(cudaMemcpy(h->d_sord, h->h_sord.data(), sizeof(int) * slist.size(), cudaMemcpyHostToDevice));
+    CIP_CUDA(cudaMemcpy(h->d_roff, h->h_roff.data(), sizeof(int) * slist.size(), cudaMemcpyHostToDevice));
+  }
   h->cd.m = m; h->cd.ncones = ncones; h->cd.type = h->d_type; h->cd.off = h->d_off;
   h->cd.row_cone = h->d_rowcone; h->cd.qlist = h->d_qlist; h->cd.nq = (int)qlist.size();
   h->cd.slist = h->d_slist; h->cd.ns = (int)slist.size(); h->cd.max_q_dim = maxq; h->cd.max_s_ord = maxs;
+  h->cd.sord = h->d_sord; h->cd.roff = h->d_roff;
   for (Scaling* S : {&h->F, &h->Fi}) {
     CIP_TRY(dev_alloc(h, &S->kind, ncones));
     CIP_TRY(dev_alloc(h, &S->a, h->m_pad + 4));
     CIP_TRY(dev_alloc(h, &S->b, h->m_pad + 4));
     CIP_TRY(dev_alloc(h, &S->D, ncones));
   }
+  CIP_TRY(dev_alloc(h, &h->F.R, h->r_total));
+  CIP_TRY(dev_alloc(h, &h->F.Ri, h->r_total));
+  h->Fi.R = h->F.R;
+  h->Fi.Ri = h->F.Ri;
 
   // ---- matrices
   const size_t nn = (size_t)h->n_pad * h->n_pad;
@@ -362,7 +407,7 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
   CIP_TRY(dev_alloc(h, &h->Qq4, nn));
   CIP_TRY(dev_alloc(h, &h->H4, nn));
   CIP_TRY(dev_alloc(h, &h->Winv, (size_t)h->n_pad * TILE));
-  CIP_TRY(dev_alloc(h, &h->info, 2));
+  CIP_TRY(dev_alloc(h, &h->info, 4));
   cudaStream_t s = h->stream;
 
   // Q
@@ -469,7 +514,7 @@ int cip_destroy(cip_handle h) {
   }
   void* ptrs[] = {h->At4, h->Atil4, h->Qq4, h->H4, h->Winv, h->G4, h->Z4, h->S4, h->Sbase4, h->WinvS, h->info,
                   h->d_type, h->d_off, h->d_rowcone, h->d_qlist, h->d_slist, h->F.kind, h->F.a, h->F.b, h->F.D,
-                  h->Fi.kind, h->Fi.a, h->Fi.b, h->Fi.D, h->partial, h->scalar};
+                  h->Fi.kind, h->Fi.a, h->Fi.b, h->Fi.D, h->partial, h->scalar, h->F.R, h->F.Ri, h->d_sord, h->d_roff};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto v : h->nv) if (v) cudaFree(v);
   for (auto v : h->mv) if (v) cudaFree(v);
@@ -543,7 +588,7 @@ int cip_nt_scaling(cip_handle h, const double* v, const double* s, double* lambd
   CIP_TRY(check(h));
   CIP_TRY(stage_in(h, h->mv[7], v, h->m));
   CIP_TRY(stage_in(h, h->mv[8], s, h->m));
-  CIP_TRY(cone_nt_scaling(h->cd, h->mv[7], h->mv[8], h->F, h->Fi, h->mv[9], h->stream));
+  CIP_TRY(cone_nt_scaling(h->cd, h->mv[7], h->mv[8], h->F, h->Fi, h->mv[9], h->info + 2, h->stream));
   h->have_scaling = true;
   CIP_TRY(stage_out(h, lambda_out, h->mv[9], h->m));
   return finish(h);
@@ -556,7 +601,6 @@ int cip_factor_from_point(cip_handle h, const double* v, const double* s, double
 }
 
 int cip_get_scaling(cip_handle h, int* kind, double* fa, double* fb, double* fD, double* fR) {
-  (void)fR;
   CIP_TRY(check(h));
   if (!h->have_scaling) { set_error("no scaling set"); return -1; }
   if (kind) {
@@ -566,6 +610,7 @@ int cip_get_scaling(cip_handle h, int* kind, double* fa, double* fb, double* fD,
   CIP_TRY(stage_out(h, fa, h->F.a, h->m));
   CIP_TRY(stage_out(h, fb, h->F.b, h->m));
   CIP_TRY(stage_out(h, fD, h->F.D, h->ncones));
+  CIP_TRY(stage_out(h, fR, h->F.R, h->r_total));     // all S cones, slist order (k*k each)
   return finish(h);
 }
 
@@ -573,8 +618,8 @@ int cip_apply(cip_handle h, int op, const double* x, double* y) {
   CIP_TRY(check(h));
   if (!h->have_scaling) { set_error("no scaling set"); return -1; }
   CIP_TRY(stage_in(h, h->mv[7], x, h->m));
-  const Scaling& S = (op == CIP_OP_F || op == CIP_OP_FT) ? h->F : h->Fi;   // R/Q blocks are symmetric
-  CIP_TRY(cone_apply(h->cd, S, h->mv[7], h->mv[8], h->stream));
+  if (op < CIP_OP_F || op > CIP_OP_FINV) { set_error("cip_apply: bad op %d", op); return -1; }
+  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, op, h->mv[7], h->mv[8], h->stream));
   CIP_TRY(stage_out(h, y, h->mv[8], h->m));
   return finish(h);
 }
@@ -622,8 +667,10 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   if (h->p) CIP_TRY(stage_in(h, h->pv[0], rw, h->p));
   CIP_TRY(stage_in(h, h->mv[0], rv, h->m));
   // t1 = F^-T (F^-T v)                                   (src/kktsolvers.jl:326)
-  CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[0], h->mv[1], s));
-  CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[1], h->mv[2], s));
+  // (= inv(F'F) v; for the non-symmetric VecCongurance blocks this is inv(F) inv(F)' v, which is
+  //  what the 3x3 system requires -- the reference's pivot is only right for symmetric F)
+  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINVT, h->mv[0], h->mv[1], s));
+  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINV, h->mv[1], h->mv[2], s));
   // rhs = y + A' t1                                      (:327)
   if (h->m) {
     CIP_TRY(q4_mv_rows(h->nv[1], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->partial, h->partial_cap, s));
@@ -646,8 +693,8 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   // dv = t1 - F^-T F^-T (A dy)                           (:328)
   if (h->m) {
     CIP_TRY(q4_mv_k(h->mv[3], h->At4, h->n_pad, h->n, h->m, h->nv[5], s));
-    CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[3], h->mv[1], s));
-    CIP_TRY(cone_apply(h->cd, h->Fi, h->mv[1], h->mv[4], s));
+    CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINVT, h->mv[3], h->mv[1], s));
+    CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINV, h->mv[1], h->mv[4], s));
     CIP_TRY(vec_axpby(h->mv[5], 1.0, h->mv[2], -1.0, h->mv[4], h->m, s));
   }
   CIP_CUDA(cudaEventRecord(h->ev[7], s));

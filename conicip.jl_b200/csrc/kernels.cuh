@@ -39,18 +39,24 @@ struct ConeDesc {
   int ns;
   int max_q_dim;
   int max_s_ord;
+  const int* sord;      // [ns] matrix order k of every S cone (slist order)
+  const int* roff;      // [ns] offset (in doubles) of its k*k block inside Scaling::R / Ri
 };
 struct Scaling {   // flattened block-diagonal operator: per cone  diag(a) + D * b b'   (kind 1) or diag(a) (kind 0)
   int* kind;       // [ncones]
   double* a;       // [m]
   double* b;       // [m]
   double* D;       // [ncones]
+  double* R;       // VecCongurance blocks (kind 2): concatenated k*k column-major R ...
+  double* Ri;      // ... and inv(R); shared between F and its inverse
 };
 
 int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling F, Scaling Fi, double* lambda,
-                    cudaStream_t st);
+                    int* info, cudaStream_t st);
 int cone_invert_scaling(const ConeDesc& c, Scaling F, Scaling Fi, cudaStream_t st);
-int cone_apply(const ConeDesc& c, Scaling F, const double* x, double* y, cudaStream_t st);
+// y = op(F) x with op in CIP_OP_{F,FT,FINVT,FINV}; Fi is the precomputed inverse of the diag/Woodbury part
+int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, const double* x, double* y,
+               cudaStream_t st);
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
 // result (device scalar) = min over cones; d == nullptr -> `nothing` variant
@@ -59,6 +65,19 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
 // Atil = F^-T A on the Q4 transposed panel (rows = columns of A, k = rows of A)
 int cone_scale_panel(const ConeDesc& c, Scaling Fi, const double* At4, double* Atil4, int ld, int m_pad,
                      int ncols, cudaStream_t st);
+
+// ---------------------------------------------------------------- S (PSD) cones (sdp.cu)
+int sdp_max_order();
+int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, const double* x, double* y,
+              cudaStream_t st);
+int sdp_nt_scaling(const ConeDesc& c, Scaling F, Scaling Fi, const double* v, const double* s, double* lambda,
+                   int* info, cudaStream_t st);
+int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st);
+int sdp_prod_div(const ConeDesc& c, const double* x, const double* y, double* o, int divide, cudaStream_t st);
+int sdp_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, unsigned long long* key,
+                cudaStream_t st);
+int sdp_scale_panel(const ConeDesc& c, const Scaling& Fi, const double* At4, double* Atil4, int ld, int ncols,
+                    cudaStream_t st);
 
 // ---------------------------------------------------------------- Cholesky (chol.cu)
 struct CholPlan {

@@ -1,0 +1,534 @@
+// S (PSD) cone kernels: VecCongurance apply, nestod_sdc, maxstep_sdc, xsdc / dsdc and the scaled
+// panel rows of S blocks.  One CTA per S cone; all k x k work (k <= 64) happens in shared memory.
+// Replaces src/ConicIP.jl:35-40,69 (VecCongurance), :93-151 (mat/vecm), :196-210 (nestod_sdc),
+// :272-303 (maxstep_sdc), :347-360 (dsdc!/xsdc!).  Dense factorizations that Julia takes from
+// LAPACK (cholesky, svd, eigvals, lyap) are done here with an in-CTA Cholesky and a one-sided
+// (Hestenes) Jacobi iteration, which has high relative accuracy for the SVD the NT scaling needs.
+#include <math_constants.h>
+
+#include "kernels.cuh"
+#include "../../include/conicip_b200.h"
+
+namespace cip {
+
+namespace {
+
+constexpr int KMAX = 64;
+constexpr int LDM = KMAX + 1;          // padded leading dimension of every shared k x k matrix
+constexpr int MAT = KMAX * LDM;        // doubles per shared matrix
+constexpr int NT = 256;                // threads per CTA
+#define SQRT2 1.4142135623730951
+#define M(A, i, j) (A)[(j) * LDM + (i)]   // column-major
+
+__device__ __forceinline__ int svec_index(int i, int j, int k) {   // i <= j, row-major upper triangle
+  return i * k - (i * (i - 1)) / 2 + (j - i);
+}
+
+// X = mat(x)   (src/ConicIP.jl:93-119)
+__device__ void load_mat(double* X, const double* __restrict__ x, int k) {
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    const double v = x[svec_index(a, b, k)];
+    M(X, i, j) = (i == j) ? v : v / SQRT2;
+  }
+}
+// y = vecm(Y)  (src/ConicIP.jl:128-151); Y is symmetrised as (Y + Y')/2 to wash out rounding asymmetry
+__device__ void store_vecm(double* __restrict__ y, const double* Y, int k, bool accumulate = false) {
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    if (i <= j) {
+      const double v = 0.5 * (M(Y, i, j) + M(Y, j, i));
+      const double o = (i == j) ? v : v * SQRT2;
+      const int idx = svec_index(i, j, k);
+      y[idx] = accumulate ? y[idx] + o : o;
+    }
+  }
+}
+// C = op(A) * op(B), k x k, all in shared memory (C must not alias A or B)
+template <bool TA, bool TB>
+__device__ void matmul(double* C, const double* A, const double* B, int k) {
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    double s = 0.0;
+    for (int l = 0; l < k; ++l) s = fma(TA ? M(A, l, i) : M(A, i, l), TB ? M(B, j, l) : M(B, l, j), s);
+    M(C, i, j) = s;
+  }
+}
+// In-place lower Cholesky of a symmetric matrix; strict upper triangle zeroed.  Returns false in
+// *ok (shared) when a pivot is not positive.
+__device__ void cholesky(double* A, int k, int* ok) {
+  if (threadIdx.x == 0) *ok = 1;
+  __syncthreads();
+  for (int c = 0; c < k; ++c) {
+    const double d = M(A, c, c);
+    __syncthreads();
+    if (!(d > 0.0)) {
+      if (threadIdx.x == 0) *ok = 0;
+      __syncthreads();
+      return;
+    }
+    const double l = sqrt(d);
+    for (int i = c + threadIdx.x; i < k; i += NT) M(A, i, c) = (i == c) ? l : M(A, i, c) / l;
+    __syncthreads();
+    for (int e = threadIdx.x; e < (k - c - 1) * (k - c - 1); e += NT) {
+      const int i = c + 1 + e % (k - c - 1), j = c + 1 + e / (k - c - 1);
+      if (i >= j) M(A, i, j) -= M(A, i, c) * M(A, j, c);
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    if (i < j) M(A, i, j) = 0.0;
+  }
+  __syncthreads();
+}
+// X = inv(L) for lower-triangular L (X lower-triangular, distinct buffer)
+__device__ void tri_inverse(double* X, const double* L, int k) {
+  for (int e = threadIdx.x; e < k * k; e += NT) M(X, e % k, e / k) = 0.0;
+  __syncthreads();
+  // column j of X solves L x = e_j; one thread per column (k <= 64 columns, forward substitution)
+  for (int j = threadIdx.x; j < k; j += NT) {
+    for (int i = j; i < k; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int l = j; l < i; ++l) s -= M(L, i, l) * M(X, l, j);
+      M(X, i, j) = s / M(L, i, i);
+    }
+  }
+  __syncthreads();
+}
+// One-sided (Hestenes) Jacobi: rotates the columns of G (and of V, if non-null, starting from
+// whatever V holds) until they are mutually orthogonal: G_out = G_in * J, V_out = V_in * J.
+// Round-robin ordering; each of the k/2 disjoint pairs of a step is handled by 8 lanes.
+__device__ void jacobi_onesided(double* G, double* V, int k, int* sh_flag) {
+  const int kk = (k + 1) & ~1;                 // even number of players (a phantom column if k is odd)
+  const int pairs = kk / 2;
+  const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 32 groups of 8 lanes
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);   // groups of one warp may diverge
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    if (threadIdx.x == 0) *sh_flag = 0;
+    __syncthreads();
+    for (int step = 0; step < kk - 1; ++step) {
+      for (int pr = grp; pr < pairs; pr += NT / 8) {
+        // round-robin tournament: player 0 fixed, others rotate
+        int p = (pr == 0) ? 0 : 1 + (pr - 1 + step) % (kk - 1);
+        int q = 1 + (kk - 2 - pr + step + (kk - 1)) % (kk - 1);
+        if (p > q) { const int t = p; p = q; q = t; }
+        const bool live = (q < k);
+        double a = 0, b = 0, g = 0;
+        if (live) {
+          for (int i = lane8; i < k; i += 8) {
+            const double gp = M(G, i, p), gq = M(G, i, q);
+            a = fma(gp, gp, a); b = fma(gq, gq, b); g = fma(gp, gq, g);
+          }
+        }
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+          a += __shfl_xor_sync(gmask, a, o);
+          b += __shfl_xor_sync(gmask, b, o);
+          g += __shfl_xor_sync(gmask, g, o);
+        }
+        if (live && fabs(g) > 1e-16 * sqrt(a * b) && g != 0.0) {
+          if (lane8 == 0) *sh_flag = 1;
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          for (int i = lane8; i < k; i += 8) {
+            const double gp = M(G, i, p), gq = M(G, i, q);
+            M(G, i, p) = c * gp - s * gq;
+            M(G, i, q) = s * gp + c * gq;
+            if (V) {
+              const double vp = M(V, i, p), vq = M(V, i, q);
+              M(V, i, p) = c * vp - s * vq;
+              M(V, i, q) = s * vp + c * vq;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const int again = *sh_flag;
+    __syncthreads();
+    if (!again) break;
+  }
+}
+
+struct SMem {
+  double* A; double* B; double* C; double* D;   // four k x k matrices
+  double* vec;                                  // KMAX doubles
+  int* flag;
+};
+__device__ __forceinline__ SMem carve(double* base) {
+  SMem s;
+  s.A = base; s.B = base + MAT; s.C = base + 2 * MAT; s.D = base + 3 * MAT;
+  s.vec = base + 4 * MAT;
+  s.flag = reinterpret_cast<int*>(s.vec + KMAX);
+  return s;
+}
+constexpr int SDP_SMEM = (4 * MAT + KMAX) * 8 + 16;
+
+// signed eigen-decomposition of a symmetric matrix Msym (in s.A, destroyed): eigenvalues -> s.vec,
+// eigenvectors -> s.B (if want_vectors).  Uses the shift M + c I (c = ||M||_F) so that the one-sided
+// Jacobi sees a PSD matrix and singular values equal eigenvalues.
+__device__ void sym_eigen(SMem s, int k, bool want_vectors) {
+  double* A = s.A; double* V = s.B;
+  double fro = 0.0;
+  for (int e = threadIdx.x; e < k * k; e += NT) { const double v = M(A, e % k, e / k); fro = fma(v, v, fro); }
+  fro = warp_sum(fro);
+  __shared__ double red[NT / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = fro;
+  __syncthreads();
+  double c = 0.0;
+  for (int i = 0; i < NT / 32; ++i) c += red[i];
+  c = sqrt(c);
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    if (i == j) M(A, i, j) += c;
+    M(V, i, j) = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  jacobi_onesided(A, V, k, s.flag);
+  // columns of A are now (lambda_j + c) v_j: lambda_j = v_j . a_j - c
+  for (int j = threadIdx.x; j < k; j += NT) {
+    double d = 0.0;
+    for (int i = 0; i < k; ++i) d = fma(M(V, i, j), M(A, i, j), d);
+    s.vec[j] = d - c;
+  }
+  __syncthreads();
+  (void)want_vectors;
+}
+
+// ------------------------------------------------------------------ kernels (grid = number of S cones)
+struct SDesc {
+  const int* slist;   // cone indices
+  const int* off;     // cone row offsets
+  const int* sord;    // order k per S cone (slist order)
+  const int* roff;    // offset (doubles) into R / Ri per S cone
+};
+
+// y_I = vecm(A' mat(x_I) A) with A = R, R', inv(R), inv(R)' selected by (use_inv, transpose)
+__global__ void __launch_bounds__(NT)
+sdp_apply_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ R, const double* __restrict__ Ri,
+                 int use_inv, int transpose, const double* __restrict__ x, double* __restrict__ y) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  if (kind[ci] != CIP_BLK_VECCONG) return;
+  const int k = d.sord[si], off = d.off[ci];
+  const double* src = (use_inv ? Ri : R) + d.roff[si];
+  for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) = src[e];
+  load_mat(s.B, x + off, k);
+  __syncthreads();
+  if (!transpose) {
+    matmul<false, false>(s.C, s.B, s.A, k);     // X A
+    __syncthreads();
+    matmul<true, false>(s.D, s.A, s.C, k);      // A' (X A)
+  } else {
+    matmul<false, true>(s.C, s.B, s.A, k);      // X A'
+    __syncthreads();
+    matmul<false, false>(s.D, s.A, s.C, k);     // A (X A')
+  }
+  __syncthreads();
+  store_vecm(y + off, s.D, k);
+}
+
+// nestod_sdc (src/ConicIP.jl:196-210): R = inv(Lz)' U sqrt(Lambda), U Lambda V' = svd(Lz' Ls);
+// also writes inv(R) = Lambda^-1/2 U' Lz' and lambda = F v = vecm(R' Z R).
+__global__ void __launch_bounds__(NT)
+sdp_nt_kernel(SDesc d, int* __restrict__ kindF, int* __restrict__ kindFi, double* __restrict__ R,
+              double* __restrict__ Ri, const double* __restrict__ v, const double* __restrict__ sv,
+              double* __restrict__ lambda, int* __restrict__ info) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  const int k = d.sord[si], off = d.off[ci];
+  load_mat(s.A, sv + off, k);      // S
+  load_mat(s.B, v + off, k);       // Z
+  __syncthreads();
+  cholesky(s.A, k, s.flag);        // Ls
+  const int ok1 = *s.flag;
+  __syncthreads();
+  cholesky(s.B, k, s.flag);        // Lz
+  const int ok2 = *s.flag;
+  __syncthreads();
+  if (!(ok1 && ok2)) {
+    if (threadIdx.x == 0) atomicCAS(info, 0, ci + 1);
+  }
+  matmul<true, false>(s.C, s.B, s.A, k);   // G = Lz' Ls
+  __syncthreads();
+  jacobi_onesided(s.C, nullptr, k, s.flag);   // C = U Sigma (columns orthogonal)
+  for (int j = threadIdx.x; j < k; j += NT) {
+    double n2 = 0.0;
+    for (int i = 0; i < k; ++i) n2 = fma(M(s.C, i, j), M(s.C, i, j), n2);
+    s.vec[j] = sqrt(n2);                    // sigma_j
+  }
+  __syncthreads();
+  tri_inverse(s.D, s.B, k);                 // D = inv(Lz)
+  // R = inv(Lz)' * (C * Sigma^-1/2)   ;   inv(R) = Sigma^-3/2 C' Lz'
+  for (int e = threadIdx.x; e < k * k; e += NT) { const int j = e / k; M(s.C, e % k, j) /= sqrt(s.vec[j]); }
+  __syncthreads();
+  matmul<true, false>(s.A, s.D, s.C, k);    // A = R
+  __syncthreads();
+  double* Rg = R + d.roff[si];
+  double* Rig = Ri + d.roff[si];
+  for (int e = threadIdx.x; e < k * k; e += NT) Rg[e] = M(s.A, e % k, e / k);
+  // inv(R) = (C Sigma^-1/2)' Lz' / sigma  (C already scaled once by Sigma^-1/2)
+  matmul<true, true>(s.D, s.C, s.B, k);     // D = C' Lz'
+  __syncthreads();
+  for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k; Rig[e] = M(s.D, i, e / k) / s.vec[i]; }
+  // lambda = vecm(R' Z R)
+  load_mat(s.B, v + off, k);
+  __syncthreads();
+  matmul<false, false>(s.C, s.B, s.A, k);
+  __syncthreads();
+  matmul<true, false>(s.D, s.A, s.C, k);
+  __syncthreads();
+  store_vecm(lambda + off, s.D, k);
+  if (threadIdx.x == 0) { kindF[ci] = CIP_BLK_VECCONG; kindFi[ci] = CIP_BLK_VECCONG; }
+}
+
+// inv(R) for user-supplied R (cip_factor / cip_set_scaling): Gauss-Jordan with partial pivoting
+__global__ void __launch_bounds__(NT)
+sdp_invert_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ R, double* __restrict__ Ri) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  if (kind[ci] != CIP_BLK_VECCONG) return;
+  const int k = d.sord[si];
+  const double* Rg = R + d.roff[si];
+  for (int e = threadIdx.x; e < k * k; e += NT) {
+    const int i = e % k, j = e / k;
+    M(s.A, i, j) = Rg[e];
+    M(s.B, i, j) = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int c = 0; c < k; ++c) {
+    if (threadIdx.x == 0) {
+      int piv = c; double best = fabs(M(s.A, c, c));
+      for (int i = c + 1; i < k; ++i) if (fabs(M(s.A, i, c)) > best) { best = fabs(M(s.A, i, c)); piv = i; }
+      *s.flag = piv;
+    }
+    __syncthreads();
+    const int piv = *s.flag;
+    if (piv != c) {
+      for (int j = threadIdx.x; j < k; j += NT) {
+        double t = M(s.A, c, j); M(s.A, c, j) = M(s.A, piv, j); M(s.A, piv, j) = t;
+        t = M(s.B, c, j); M(s.B, c, j) = M(s.B, piv, j); M(s.B, piv, j) = t;
+      }
+    }
+    __syncthreads();
+    const double pv = M(s.A, c, c);
+    for (int i = threadIdx.x; i < k; i += NT) s.vec[i] = (i == c) ? 0.0 : M(s.A, i, c) / pv;
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += NT) {
+      const int i = e % k, j = e / k;
+      const double f = s.vec[i];
+      if (i != c) { M(s.A, i, j) -= f * M(s.A, c, j); M(s.B, i, j) -= f * M(s.B, c, j); }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += NT) { M(s.A, c, j) /= pv; M(s.B, c, j) /= pv; }
+    __syncthreads();
+  }
+  double* Rig = Ri + d.roff[si];
+  for (int e = threadIdx.x; e < k * k; e += NT) Rig[e] = M(s.B, e % k, e / k);
+}
+
+// o = vecm(XY + YX)  (xsdc!, :355-360)   /   o = vecm(O), Y O + O Y = X  (dsdc!, :347-353)
+__global__ void __launch_bounds__(NT)
+sdp_prod_div_kernel(SDesc d, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o,
+                    int divide) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  const int k = d.sord[si], off = d.off[ci];
+  if (!divide) {
+    load_mat(s.A, x + off, k);
+    load_mat(s.B, y + off, k);
+    __syncthreads();
+    matmul<false, false>(s.C, s.A, s.B, k);
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k, j = e / k; M(s.D, i, j) = M(s.C, i, j) + M(s.C, j, i); }
+    __syncthreads();
+    store_vecm(o + off, s.D, k);
+    return;
+  }
+  // Y = V diag(l) V';  T = V' X V;  T_ij /= (l_i + l_j);  O = V T V'
+  load_mat(s.A, y + off, k);
+  __syncthreads();
+  sym_eigen(s, k, true);                       // eigenvalues s.vec, vectors s.B
+  load_mat(s.A, x + off, k);
+  __syncthreads();
+  matmul<false, false>(s.C, s.A, s.B, k);      // X V
+  __syncthreads();
+  matmul<true, false>(s.D, s.B, s.C, k);       // V' X V
+  __syncthreads();
+  for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k, j = e / k; M(s.D, i, j) /= (s.vec[i] + s.vec[j]); }
+  __syncthreads();
+  matmul<false, true>(s.C, s.D, s.B, k);       // T V'
+  __syncthreads();
+  matmul<false, false>(s.A, s.B, s.C, k);      // V T V'
+  __syncthreads();
+  store_vecm(o + off, s.A, k);
+}
+
+__device__ __forceinline__ unsigned long long dkey2(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// maxstep_sdc (:272-303)
+__global__ void __launch_bounds__(NT)
+sdp_maxstep_kernel(SDesc d, const double* __restrict__ x, const double* __restrict__ dd, double d_scale,
+                   unsigned long long* key) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  const int k = d.sord[si], off = d.off[ci];
+  double res;
+  if (!dd) {                                       // minimum eigenvalue of X
+    load_mat(s.A, x + off, k);
+    __syncthreads();
+    sym_eigen(s, k, false);
+    double mn = CUDART_INF;
+    for (int j = 0; j < k; ++j) mn = fmin(mn, s.vec[j]);
+    res = mn > 0 ? 0.0 : -1.0 + mn;
+  } else {
+    load_mat(s.C, x + off, k);
+    __syncthreads();
+    cholesky(s.C, k, s.flag);                      // X = L L'
+    const int ok = *s.flag;
+    __syncthreads();
+    if (!ok) {
+      res = CUDART_INF;                            // X not positive definite (:277-280)
+    } else {
+      tri_inverse(s.D, s.C, k);                    // inv(L)
+      load_mat(s.A, dd + off, k);
+      __syncthreads();
+      for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) /= d_scale;
+      __syncthreads();
+      matmul<false, true>(s.B, s.A, s.D, k);       // D inv(L)'
+      __syncthreads();
+      matmul<false, false>(s.A, s.D, s.B, k);      // inv(L) D inv(L)'  (similar to X^-1/2 D X^-1/2)
+      __syncthreads();
+      for (int e = threadIdx.x; e < k * k; e += NT) {   // symmetrise, :284
+        const int i = e % k, j = e / k;
+        if (i < j) { const double m = 0.5 * (M(s.A, i, j) + M(s.A, j, i)); M(s.A, i, j) = m; M(s.A, j, i) = m; }
+      }
+      __syncthreads();
+      sym_eigen(s, k, false);
+      double mx = -CUDART_INF;
+      for (int j = 0; j < k; ++j) mx = fmax(mx, s.vec[j]);
+      res = (mx < 0) ? CUDART_INF : 1.0 / mx;
+    }
+  }
+  if (threadIdx.x == 0 && res < CUDART_INF) atomicMin(key, dkey2(res));
+}
+
+// Atil rows of an S block: column j of A restricted to the block, a_j -> vecm(inv(R) mat(a_j) inv(R)')
+// grid (S cone, column chunk); each CTA keeps inv(R) resident and loops over its columns.
+__global__ void __launch_bounds__(NT)
+sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ Ri,
+                       const double* __restrict__ At4, double* __restrict__ Atil4, int ld, int ncols,
+                       int cols_per_cta) {
+  extern __shared__ double smem[];
+  SMem s = carve(smem);
+  const int si = blockIdx.x, ci = d.slist[si];
+  if (kind[ci] != CIP_BLK_VECCONG) return;
+  const int k = d.sord[si], off = d.off[ci];
+  const int dim = k * (k + 1) / 2;
+  const double* src = Ri + d.roff[si];
+  for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) = src[e];
+  const int j0 = blockIdx.y * cols_per_cta;
+  const int j1 = min(ncols, j0 + cols_per_cta);
+  for (int j = j0; j < j1; ++j) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += NT) {
+      const int i = e % k, c = e / k;
+      const int a = i < c ? i : c, b = i < c ? c : i;
+      const double v = At4[q4_index(j, off + svec_index(a, b, k), ld)];
+      M(s.B, i, c) = (i == c) ? v : v / SQRT2;
+    }
+    __syncthreads();
+    matmul<false, true>(s.C, s.B, s.A, k);      // X inv(R)'
+    __syncthreads();
+    matmul<false, false>(s.D, s.A, s.C, k);     // inv(R) X inv(R)'
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += NT) {
+      const int i = e % k, c = e / k;
+      if (i <= c) {
+        const double v = 0.5 * (M(s.D, i, c) + M(s.D, c, i));
+        Atil4[q4_index(j, off + svec_index(i, c, k), ld)] = (i == c) ? v : v * SQRT2;
+      }
+    }
+  }
+  (void)dim;
+}
+
+bool g_attr = false;
+int set_attrs() {
+  if (g_attr) return 0;
+  CIP_CUDA(cudaFuncSetAttribute(sdp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  CIP_CUDA(cudaFuncSetAttribute(sdp_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  CIP_CUDA(cudaFuncSetAttribute(sdp_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  CIP_CUDA(cudaFuncSetAttribute(sdp_prod_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  CIP_CUDA(cudaFuncSetAttribute(sdp_maxstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  CIP_CUDA(cudaFuncSetAttribute(sdp_scale_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
+  g_attr = true;
+  return 0;
+}
+SDesc sdesc(const ConeDesc& c) { return SDesc{c.slist, c.off, c.sord, c.roff}; }
+
+}  // namespace
+
+int sdp_max_order() { return KMAX; }
+
+int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, const double* x, double* y,
+              cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  sdp_apply_kernel<<<c.ns, NT, SDP_SMEM, st>>>(sdesc(c), F.kind, F.R, F.Ri, use_inv, transpose, x, y);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+int sdp_nt_scaling(const ConeDesc& c, Scaling F, Scaling Fi, const double* v, const double* s, double* lambda,
+                   int* info, cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  sdp_nt_kernel<<<c.ns, NT, SDP_SMEM, st>>>(sdesc(c), F.kind, Fi.kind, F.R, F.Ri, v, s, lambda, info);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  sdp_invert_kernel<<<c.ns, NT, SDP_SMEM, st>>>(sdesc(c), F.kind, F.R, F.Ri);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+int sdp_prod_div(const ConeDesc& c, const double* x, const double* y, double* o, int divide, cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  sdp_prod_div_kernel<<<c.ns, NT, SDP_SMEM, st>>>(sdesc(c), x, y, o, divide);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+int sdp_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, unsigned long long* key,
+                cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  sdp_maxstep_kernel<<<c.ns, NT, SDP_SMEM, st>>>(sdesc(c), x, d, d_scale, key);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+int sdp_scale_panel(const ConeDesc& c, const Scaling& Fi, const double* At4, double* Atil4, int ld, int ncols,
+                    cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  CIP_TRY(set_attrs());
+  const int per = 16;
+  dim3 grid(c.ns, (ncols + per - 1) / per);
+  sdp_scale_panel_kernel<<<grid, NT, SDP_SMEM, st>>>(sdesc(c), Fi.kind, Fi.Ri, At4, Atil4, ld, ncols, per);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cip

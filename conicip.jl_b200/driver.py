@@ -95,9 +95,6 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
     block_types = [t for t, _ in cone_dims]
     block_sizes = [int(k) for _, k in cone_dims]
     offs = np.concatenate([[0], np.cumsum(block_sizes)]).astype(int)
-    if any(t == "S" for t in block_types):
-        raise NotImplementedError("S cones are not available in this build of the B200 engine")
-
     # conedim / e, src/ConicIP.jl:547-565 (conedim is global under sharding)
     e_h = np.zeros(m)
     conedim = 0
@@ -105,9 +102,17 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
         if t == "R":
             conedim += k
             e_h[o:o + k] = 1.0
-        else:
+        elif t == "Q":
             conedim += 1
             e_h[o] = 1.0
+        else:                                    # S: vecm(I), src/ConicIP.jl:551,564
+            ks = int(round((math.sqrt(1 + 8 * k) - 1) / 2))
+            conedim += ks
+            idx, pos = 0, []
+            for i in range(ks):
+                pos.append(o + idx)
+                idx += ks - i
+            e_h[pos] = 1.0
     conedim = int(round(R.sum(float(conedim))))
 
     c_t, b_t, d_t, e_t = T(c_h), T(b_h), T(d_h), T(e_h)

@@ -17,6 +17,10 @@ def _is_torch(x):
     return hasattr(x, "data_ptr")
 
 
+def _s_order(dim):
+    return int(round((np.sqrt(1 + 8 * dim) - 1) / 2))
+
+
 def _colmajor(M):
     """Dense column-major float64 (Julia layout) from dense / scipy.sparse / torch input."""
     if M is None:
@@ -194,11 +198,20 @@ class Engine:
         check(lib().cip_set_scaling(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data,
                                     None if fR is None else fR.ctypes.data))
 
-    def get_scaling(self):
+    def get_scaling(self, with_R=False):
         nc = len(self.cone_dims)
         kind = np.zeros(nc, dtype=np.int32)
         fa, fb, fD = np.zeros(self.m), np.zeros(self.m), np.zeros(nc)
-        check(lib().cip_get_scaling(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data, None))
+        orders = [_s_order(k) for t, k in self.cone_dims if t == "S"]
+        fR = np.zeros(max(1, sum(k * k for k in orders)))
+        check(lib().cip_get_scaling(self._h, kind.ctypes.data, fa.ctypes.data, fb.ctypes.data, fD.ctypes.data,
+                                    fR.ctypes.data if orders else None))
+        if with_R:
+            Rs, o = [], 0
+            for k in orders:
+                Rs.append(fR[o:o + k * k].reshape(k, k, order="F").copy())
+                o += k * k
+            return kind, fa, fb, fD, Rs
         return kind, fa, fb, fD
 
     # ------------------------------------------------------------------ LEVEL 3

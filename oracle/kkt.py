@@ -134,8 +134,10 @@ def kktsolver_chol(Q, A, G, cone_dims):
             t = sla.solve_triangular(L, r, lower=True, check_finite=False)
             return sla.solve_triangular(L.T, t, lower=False, check_finite=False)
 
+        Finv = F.inv()
+
         def solve3x3(y, w, v):
-            t1 = Finvt.mul(Finvt.mul(v))
+            t1 = Finv.mul(Finvt.mul(v))              # inv(F'F) v (== pivot's F^-T F^-T v for symmetric F)
             ry = y + A.T @ t1
             if p:
                 u = hsolve(ry)
@@ -146,7 +148,7 @@ def kktsolver_chol(Q, A, G, cone_dims):
             else:
                 dy = hsolve(ry)
                 dw = np.zeros(0)
-            dv = t1 - Finvt.mul(Finvt.mul(A @ dy))
+            dv = t1 - Finv.mul(Finvt.mul(A @ dy))
             return dy, dw, dv
 
         return solve3x3

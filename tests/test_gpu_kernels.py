@@ -267,11 +267,6 @@ def test_error_behaviour():
     st = eng.factor(cb.Block([cb.Diagonal(np.ones(2))]))
     assert st == 1 and "pivot" in cb._lib.last_error()
     eng.close()
-    # S cones are not in this build: loud error, not a silent fallback
-    eng = cb.Engine(np.eye(3), np.ones((3, 3)), None, [("S", 3)])
-    with pytest.raises(cb.CipError):
-        eng.nt_scaling(np.ones(3), np.ones(3))
-    eng.close()
 
 
 def test_regularisation_option():

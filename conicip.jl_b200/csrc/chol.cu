@@ -9,14 +9,38 @@ namespace cip {
 
 namespace {
 constexpr int NB = 128;
-constexpr int SLD = 132;  // padded row stride of the shared 128x128 block
+constexpr int SLD = 129;  // padded (odd) row stride of the shared 128x128 block: column walks are conflict-free
+
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));   // ~20 bits; two Newton steps -> full double
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
+// Cholesky factor L and inverse inv(L) of one 128x128 diagonal block, one CTA of 512 threads.
+//   * four 32-column sub-panels; inside a sub-panel every thread keeps its 8 matrix elements in
+//     registers and only the current column travels through shared memory (double-buffered, one
+//     barrier per column); the pivot scaling is deferred (S[i][j] -= S[i][k] S[j][k] / d_k) so the
+//     dependent chain per column is LDS -> rcp -> FMA.  Rows below the 32x32 diagonal block are
+//     eliminated in the same sweep, i.e. the in-block TRSM comes for free.
+//   * rank-32 update of the remaining columns from a transposed copy of the sub-panel (4x4 register
+//     tiles, conflict-free 32-byte loads).
+//   * inv(L): the four 32x32 diagonal blocks by 4-lane column groups, then the off-diagonal blocks
+//     X_ij = -X_ii * sum_k L_ik X_kj by block distance.  X is kept transposed in the free upper
+//     triangle of S.
+constexpr int SB = 32;           // sub-panel width
+constexpr int PLD = 132;         // leading dimension of the transposed sub-panel copy P[k][i]
 
 __global__ void __launch_bounds__(512, 1)
 potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W, int* info) {
-  extern __shared__ double S[];        // S[r * SLD + c]; lower triangle: factor, upper triangle: inverse^T
-  double* dinv = S + NB * SLD;         // [NB] 1/d_k during the factorisation, then 1/L_kk
-  double* rsq = dinv + NB;             // [NB] 1/sqrt(d_k)
-  const int tid = threadIdx.x;
+  extern __shared__ double S[];                  // S[r * SLD + c]
+  double* dinv = S + NB * SLD;                   // [NB]   1 / L_kk
+  double* colk = dinv + NB;                      // [2][NB] travelling column (double-buffered)
+  double* P = colk + 2 * NB;                     // [SB][PLD] transposed sub-panel; later block temporaries
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   {
     const int r = tid & 127;
     for (int q = tid >> 7; q < 32; q += 4) {
@@ -28,74 +52,150 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   }
   __syncthreads();
 
-  // ---- right-looking Cholesky with deferred column scaling: column k keeps L[:,k]*L[k,k] until the
-  //      end, the trailing update uses S[r][k]*S[c][k]/d_k, so each step needs a single barrier.
-  {
-    const int c = tid & 127, rg = tid >> 7;
-    for (int k = 0; k < NB - 1; ++k) {
-      double d = S[k * SLD + k];
-      if (!(d > 0.0)) {
-        if (tid == 0) atomicCAS(info, 0, j0 + k + 1);
-        d = 1.0;
-      }
-      const double id = 1.0 / d;
-      if (c > k) {
-        const double t = S[c * SLD + k] * id;
-        int r = c + ((rg - c) & 3);          // first row >= c with r % 4 == rg
-#pragma unroll 4
-        for (; r < NB; r += 4) S[r * SLD + c] = fma(-S[r * SLD + k], t, S[r * SLD + c]);
+  for (int c0 = 0; c0 < NB; c0 += SB) {
+    // ---- sub-panel: column j = c0 + lane, rows i_e = w + 16 e
+    const int j = c0 + lane;
+    double a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = w + 16 * e;
+      a[e] = (i >= j) ? S[i * SLD + j] : 0.0;
+    }
+    double dj = 1.0;
+    for (int k = 0; k < SB; ++k) {
+      double* ck = colk + (k & 1) * NB;
+      if (lane == k) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ck[w + 16 * e] = a[e];
       }
       __syncthreads();
-    }
-    if (tid < NB) {
-      double d = S[tid * SLD + tid];
+      double d = ck[c0 + k];
       if (!(d > 0.0)) {
-        atomicCAS(info, 0, j0 + tid + 1);
+        if (tid == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
         d = 1.0;
       }
-      const double l = sqrt(d);
-      rsq[tid] = 1.0 / l;
-      dinv[tid] = 1.0 / l;                    // 1 / L_kk
+      if (lane == k) dj = d;
+      if (lane > k) {
+        const double t = ck[j] * fast_rcp(d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int i = w + 16 * e;
+          if (i >= j) a[e] = fma(-ck[i], t, a[e]);
+        }
+      }
+    }
+    // scale: L[i][j] = a / sqrt(d_j); publish to S and to the transposed copy P[lane][i]
+    {
+      const double rs = 1.0 / sqrt(dj);
+      if (w == (j & 15)) dinv[j] = rs;             // exactly one thread per column (the owner of (j,j))
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = w + 16 * e;
+        double v = 0.0;
+        if (i > j) v = a[e] * rs;
+        else if (i == j) v = dj * rs;
+        if (i >= c0) {
+          S[i * SLD + j] = v;
+          P[lane * PLD + i] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rank-32 update of the columns right of the sub-panel: 4x4 register tiles, lower part
+    const int R = NB - c0 - SB;                    // remaining order
+    if (R > 0) {
+      const int nt4 = R / 4;
+      const int ntile = nt4 * (nt4 + 1) / 2;
+      for (int t = tid; t < ntile; t += 512) {
+        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const int i0 = c0 + SB + 4 * ti, jj0 = c0 + SB + 4 * tj;
+        double acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < SB; ++k) {
+          const double2 p0 = *reinterpret_cast<const double2*>(P + k * PLD + i0);
+          const double2 p1 = *reinterpret_cast<const double2*>(P + k * PLD + i0 + 2);
+          const double2 q0 = *reinterpret_cast<const double2*>(P + k * PLD + jj0);
+          const double2 q1 = *reinterpret_cast<const double2*>(P + k * PLD + jj0 + 2);
+          const double li[4] = {p0.x, p0.y, p1.x, p1.y}, lj[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fma(li[x], lj[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y)
+            if (i0 + x >= jj0 + y) S[(i0 + x) * SLD + jj0 + y] -= acc[x][y];
+      }
     }
     __syncthreads();
   }
-  // scale the columns (L[r][k] = S[r][k] / sqrt(d_k)), zero the strict upper triangle, write L back
+
+  // ---- write L back (strict upper triangle as zeros)
   {
     const int r = tid & 127;
     for (int q = tid >> 7; q < 32; q += 4) {
-      double* d = S + r * SLD + 4 * q;
+      double o[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int cc = 4 * q + t;
-        d[t] = (cc > r) ? 0.0 : ((cc == r) ? 1.0 / rsq[cc] : d[t] * rsq[cc]);
-      }
+      for (int t = 0; t < 4; ++t) o[t] = (4 * q + t > r) ? 0.0 : S[r * SLD + 4 * q + t];
       double2* p = reinterpret_cast<double2*>(H + ((size_t)(j0 / 4 + q) * ld + j0 + r) * 4);
-      p[0] = make_double2(d[0], d[1]);
-      p[1] = make_double2(d[2], d[3]);
+      p[0] = make_double2(o[0], o[1]);
+      p[1] = make_double2(o[2], o[3]);
     }
   }
   __syncthreads();
 
-  // ---- inverse X = L^-1, column by column: a 4-lane group owns column j and walks down the rows
-  //      with no block barrier; X[i][j] is kept transposed in the (free) upper triangle S[j][i].
+  // ---- inverse.  X(r,c), r > c, lives at S[c][r]; X(r,r) = dinv[r].
+#define XG(r, c) S[(c) * SLD + (r)]
   {
-    const int j = tid >> 2, part = tid & 3;
-    const unsigned gmask = 0xFu << ((tid & 31) & ~3);
-    double* Xj = S + j * SLD;                 // Xj[i] = X[i][j]  (i > j), diagonal in xjj
-    const double xjj = dinv[j];
-    for (int i = j + 1; i < NB; ++i) {
+    // diagonal 32x32 blocks: 4 blocks x 32 columns x 4 lanes = 512 threads, no block barrier
+    const int blk = tid >> 7, jl = (tid & 127) >> 2, part = tid & 3;
+    const unsigned gmask = 0xFu << (lane & ~3);
+    const int b0 = blk * SB, jc = b0 + jl;
+    const double xjj = dinv[jc];
+    for (int i = jc + 1; i < b0 + SB; ++i) {
       const double* Li = S + i * SLD;
-      double sum = (part == 0) ? Li[j] * xjj : 0.0;
-      for (int k = j + 1 + part; k < i; k += 4) sum = fma(Li[k], Xj[k], sum);
+      double sum = (part == 0) ? Li[jc] * xjj : 0.0;
+      for (int k = jc + 1 + part; k < i; k += 4) sum = fma(Li[k], XG(k, jc), sum);
       sum += __shfl_xor_sync(gmask, sum, 1);
       sum += __shfl_xor_sync(gmask, sum, 2);
-      if (part == 0) Xj[i] = -sum * dinv[i];
+      if (part == 0) XG(i, jc) = -sum * dinv[i];
       __syncwarp(gmask);
     }
   }
   __syncthreads();
+  for (int dlt = 1; dlt < NB / SB; ++dlt) {
+    const int nblk = NB / SB - dlt;
+    // T_b = sum_{kk} L(ib, kk) * X(kk, jb)   for block pairs (ib, jb) = (b + dlt, b)
+    for (int o = tid; o < nblk * SB * SB; o += 512) {
+      const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
+      const int ri = (b + dlt) * SB + r, cj = b * SB + c;
+      const double* Li = S + ri * SLD;
+      double sum = Li[cj] * dinv[cj];
+      for (int kk = cj + 1; kk < (b + dlt) * SB; ++kk) sum = fma(Li[kk], XG(kk, cj), sum);
+      P[(b * SB + r) * SB + c] = sum;
+    }
+    __syncthreads();
+    // X_ib,jb = - X_ib,ib * T_b
+    for (int o = tid; o < nblk * SB * SB; o += 512) {
+      const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
+      const int i0 = (b + dlt) * SB;
+      double sum = dinv[i0 + r] * P[(b * SB + r) * SB + c];
+      for (int k = 0; k < r; ++k) sum = fma(XG(i0 + r, i0 + k), P[(b * SB + k) * SB + c], sum);
+      XG(i0 + r, b * SB + c) = -sum;
+    }
+    __syncthreads();
+  }
   {
-    // W[r][c] = X[r][c] = (c < r) ? S[c][r] : (c == r ? dinv[r] : 0)
+    // W[r][c] = X(r,c) = (c < r) ? S[c][r] : (c == r ? dinv[r] : 0)
     const int r = tid & 127;
     for (int q = tid >> 7; q < 32; q += 4) {
       double o[4];
@@ -109,6 +209,7 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
       p[1] = make_double2(o[2], o[3]);
     }
   }
+#undef XG
 }
 
 // forward sweep step for panel jb:  y_j = inv(L_jj) b_j ;  b_i -= L_ij y_j  (i > j)
@@ -253,7 +354,7 @@ void chol_free_plan(CholPlan* p) {
 //   high-priority stream `sc`, so its factorisation overlaps the bulk update running on `s`.
 int chol_factor(const CholPlan& p, cudaStream_t s) {
   constexpr int OUTER = 4;
-  const int smem = (NB * SLD + 2 * NB) * (int)sizeof(double);
+  const int smem = (NB * SLD + 3 * NB + SB * PLD) * (int)sizeof(double);
   if (!g_potrf_attr) {
     CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     g_potrf_attr = true;

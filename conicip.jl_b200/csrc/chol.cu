@@ -179,18 +179,36 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
       const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
       const int ri = (b + dlt) * SB + r, cj = b * SB + c;
       const double* Li = S + ri * SLD;
-      double sum = Li[cj] * dinv[cj];
-      for (int kk = cj + 1; kk < (b + dlt) * SB; ++kk) sum = fma(Li[kk], XG(kk, cj), sum);
-      P[(b * SB + r) * SB + c] = sum;
+      // four independent partial sums: the dependent-FMA chain, not the loads, bounds this loop
+      double s0 = Li[cj] * dinv[cj], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double* Xc = S + cj * SLD;                      // XG(kk, cj) = Xc[kk]
+      const int kend = (b + dlt) * SB;
+      int kk = cj + 1;
+      for (; kk + 3 < kend; kk += 4) {
+        s0 = fma(Li[kk], Xc[kk], s0);
+        s1 = fma(Li[kk + 1], Xc[kk + 1], s1);
+        s2 = fma(Li[kk + 2], Xc[kk + 2], s2);
+        s3 = fma(Li[kk + 3], Xc[kk + 3], s3);
+      }
+      for (; kk < kend; ++kk) s0 = fma(Li[kk], Xc[kk], s0);
+      P[(b * SB + r) * SB + c] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     // X_ib,jb = - X_ib,ib * T_b
     for (int o = tid; o < nblk * SB * SB; o += 512) {
       const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
       const int i0 = (b + dlt) * SB;
-      double sum = dinv[i0 + r] * P[(b * SB + r) * SB + c];
-      for (int k = 0; k < r; ++k) sum = fma(XG(i0 + r, i0 + k), P[(b * SB + k) * SB + c], sum);
-      XG(i0 + r, b * SB + c) = -sum;
+      double s0 = dinv[i0 + r] * P[(b * SB + r) * SB + c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      const double* Pc = P + (b * SB) * SB + c;             // Pc[k * SB] = T_b[k][c]
+      int k = 0;
+      for (; k + 3 < r; k += 4) {
+        s0 = fma(XG(i0 + r, i0 + k), Pc[k * SB], s0);
+        s1 = fma(XG(i0 + r, i0 + k + 1), Pc[(k + 1) * SB], s1);
+        s2 = fma(XG(i0 + r, i0 + k + 2), Pc[(k + 2) * SB], s2);
+        s3 = fma(XG(i0 + r, i0 + k + 3), Pc[(k + 3) * SB], s3);
+      }
+      for (; k < r; ++k) s0 = fma(XG(i0 + r, i0 + k), Pc[k * SB], s0);
+      XG(i0 + r, b * SB + c) = -((s0 + s1) + (s2 + s3));
     }
     __syncthreads();
   }

@@ -360,7 +360,10 @@ def run_b200(args, n, m):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per SYRK launch from the committed ncu --set full
 # capture (profiles/), keyed by (n, rows on the GPU); None where no capture exists.
-TRAFFIC_BYTES = {}
+TRAFFIC_BYTES = {
+    (16384, 262144): 811.947289e9 + 1.196444e9,   # profiles/r01_ncu_syrk_band.md (C4, one GPU)
+    (8192, 16384): 6.703572e9 + 0.270010e9,       # same file (C2)
+}
 
 
 def main():

@@ -64,6 +64,21 @@ class TorchReducer:
     def min(self, x):
         return self._red(x, self._d.ReduceOp.MIN)
 
+    def sum_tensor_(self, t):
+        """In-place sum of a small device (nccl) or host (gloo) tensor across ranks."""
+        if t.device.type != self._dev:
+            u = t.to(self._dev)
+            self._d.all_reduce(u, op=self._d.ReduceOp.SUM, group=self._g)
+            t.copy_(u)
+        else:
+            self._d.all_reduce(t, op=self._d.ReduceOp.SUM, group=self._g)
+        return t
+
+    def min_list(self, xs):
+        t = self._t.tensor(list(xs), dtype=self._t.float64, device=self._dev)
+        self._d.all_reduce(t, op=self._d.ReduceOp.MIN, group=self._g)
+        return t.tolist()
+
 
 def init_engine_comm(engine, group=None):
     """Create the NCCL communicator inside the engine: rank 0 makes the unique id, the host

@@ -56,6 +56,12 @@ class LocalReducer:
     def min(self, x):
         return x
 
+    def sum_tensor_(self, t):
+        return t
+
+    def min_list(self, xs):
+        return list(xs)
+
 
 def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
             optTol=1e-6, DTB=0.01, verbose=False, maxRefinementSteps=3, maxIters=100,
@@ -117,17 +123,27 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
 
     c_t, b_t, d_t, e_t = T(c_h), T(b_h), T(d_h), T(e_h)
 
-    def dot(x, y):
-        return float(torch.dot(x, y).item()) if x.numel() else 0.0
+    zero = torch.zeros((), dtype=f64, device=dev)
+    m_glob = int(round(R.sum(float(m))))
 
-    def mdot(x, y):
-        return R.sum(dot(x, y))
+    def dots(local_pairs, shard_pairs=()):
+        """All the inner products of one phase with ONE host synchronisation: `local_pairs` are
+        replicated n-/p-vectors, `shard_pairs` are m-vectors whose partial sums are all-reduced
+        across the row shards (one small collective) before the single device->host read."""
+        vals = [torch.dot(x, y) if x.numel() else zero for x, y in local_pairs]
+        nl = len(vals)
+        vals += [torch.dot(x, y) if x.numel() else zero for x, y in shard_pairs]
+        t = torch.stack(vals)
+        if len(shard_pairs):
+            R.sum_tensor_(t[nl:])
+        out = t.tolist()
+        return out[:nl], out[nl:]
 
     def nrm(x):
         return float(torch.linalg.vector_norm(x).item()) if x.numel() else 0.0
 
     def mnrm(x):
-        return math.sqrt(R.sum(dot(x, x)))
+        return math.sqrt(dots((), ((x, x),))[1][0])
 
     normc = nrm(c_t)
     normd = -math.inf if p == 0 else nrm(d_t)
@@ -136,8 +152,8 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
     solve3x3gen = kktsolver(Q, A, G, cone_dims)                      # :667  LEVEL 1
     eng = solve3x3gen.engine
 
-    def maxstep(x, dd, scale=1.0):                                   # :571-587
-        return R.min(eng.maxstep(x, dd, scale))
+    def maxstep2(x1, d1, x2, d2, scale=1.0):                         # :571-587, two calls, one reduction
+        return R.min_list([eng.maxstep(x1, d1, scale), eng.maxstep(x2, d2, scale)])
 
     counters = {"solves": 0, "factors": 0}
 
@@ -160,8 +176,7 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
     I0 = Block([Diagonal(np.ones(k)) for k in block_sizes])
     r0 = _V4(c_t, d_t, b_t, torch.zeros(m, dtype=f64, device=dev))
     z = solve4x4gen(e_t, I0, I0)(r0)
-    a_v = maxstep(z.v, None)
-    a_s = maxstep(z.s, None)
+    a_v, a_s = maxstep2(z.v, None, z.s, None)
     z.v = z.v - a_v * e_t
     z.s = z.s - a_s * e_t
 
@@ -190,12 +205,16 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
         rleft = _V4(Qy + Gtw - Atv, eng.mul_G(z.y), Ay - z.s, eng.cone_prod(lam, lam))
         r0 = _V4(rleft.y - c_t, rleft.w - d_t, rleft.v - b_t, rleft.s)   # :753
 
-        mubar = mdot(z.v, z.s)
+        gtw_atv = Gtw - Atv
+        ay_s = Ay - z.s
+        (cty, r0y2, yQy, w_r0w, dtw, gta2, yy, gy2, qy2), (mubar, r0v2, r0s2, v_r0v, btv, vv, ays2) = dots(
+            ((c_t, z.y), (r0.y, r0.y), (z.y, Qy), (z.w, r0.w), (d_t, z.w), (gtw_atv, gtw_atv), (z.y, z.y),
+             (rleft.w, rleft.w), (Qy, Qy)),
+            ((z.v, z.s), (r0.v, r0.v), (r0.s, r0.s), (z.v, r0.v), (b_t, z.v), (z.v, z.v), (ay_s, ay_s)))
         mu = mubar / conedim
-        cty = dot(c_t, z.y)
-        rDu = nrm(r0.y) / (1 + normc)
-        rPr = mnrm(r0.v) / (1 + normb)
-        rCp = mnrm(r0.s) / (1 + abs(cty))
+        rDu = math.sqrt(r0y2) / (1 + normc)
+        rPr = math.sqrt(r0v2) / (1 + normb)
+        rCp = math.sqrt(r0s2) / (1 + abs(cty))
         sol.trace.append((Iter, mu, rDu, rPr, rCp))
 
         if max(rDu, rPr, rCp) < optBest:                             # :768-773
@@ -203,8 +222,8 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
             sol.duFeas, sol.prFeas, sol.muFeas = rDu, rPr, rCp
             optBest = max(rDu, rPr, rCp)
 
-        pobj = 0.5 * dot(z.y, Qy) - cty
-        dobj = pobj + dot(z.w, r0.w) + mdot(z.v, r0.v) - mubar
+        pobj = 0.5 * yQy - cty
+        dobj = pobj + w_r0w + v_r0v - mubar
         sol.pobj, sol.dobj = pobj, dobj
 
         status = "None"
@@ -213,11 +232,11 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
             status = "Optimal"
 
         if not (p == 0 and m == 0):                                  # :790-852
-            dty_btv = dot(d_t, z.w) - mdot(b_t, z.v)
-            p_unscaled = nrm(Gtw - Atv)
+            dty_btv = dtw - btv
+            p_unscaled = math.sqrt(gta2)
             if dty_btv < 0:
                 with np.errstate(all="ignore"):
-                    p_cvx = np.float64(p_unscaled) / (nrm(z.y) + mnrm(z.v))
+                    p_cvx = np.float64(p_unscaled) / (math.sqrt(yy) + math.sqrt(vv))
                     p_ecos = np.float64(p_unscaled) / (max(1, normc) * abs(dty_btv))
             else:
                 p_cvx = p_ecos = nan
@@ -228,12 +247,12 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
                 out_v = z.v / -dty_btv
                 status = "Infeasible"
 
-            d1 = -math.inf if m == 0 and R.nranks == 1 else mnrm(Ay - z.s)
-            d2 = -math.inf if p == 0 else nrm(rleft.w)
-            d3 = nrm(Qy) if bool(torch.isfinite(z.y).all().item()) else nan
+            d1 = -math.inf if m_glob == 0 else math.sqrt(ays2)
+            d2 = -math.inf if p == 0 else math.sqrt(gy2)
+            d3 = math.sqrt(qy2) if math.isfinite(yy) else nan
             if cty > 0:
                 d_cvx = max(d1 / max(1, normb), d2 / max(1, normd), d3 / max(1, normc)) / abs(cty)
-                d_ecos = max(d1, d2, d3) / nrm(z.y)
+                d_ecos = max(d1, d2, d3) / math.sqrt(yy)
             else:
                 d_cvx = d_ecos = nan
             d_infeas = abs(float(np.maximum(d_cvx, d_ecos)))
@@ -254,10 +273,11 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
 
         # ---- predictor :879-887
         d_aff = solve(r0)
-        a_aff = min(min(maxstep(z.v, d_aff.v), 1), min(maxstep(z.s, d_aff.s), 1))
+        a1, a2 = maxstep2(z.v, d_aff.v, z.s, d_aff.s)
+        a_aff = min(min(a1, 1), min(a2, 1))
         # fts(), :162-163
-        rho = (mdot(z.v, z.s) - a_aff * mdot(z.v, d_aff.s) - a_aff * mdot(d_aff.v, z.s)
-               + a_aff * a_aff * mdot(d_aff.v, d_aff.s)) / mubar
+        _, (v_ds, dv_s, dv_ds) = dots((), ((z.v, d_aff.s), (d_aff.v, z.s), (d_aff.v, d_aff.s)))
+        rho = (mubar - a_aff * v_ds - a_aff * dv_s + a_aff * a_aff * dv_ds) / mubar
         sigma = max(0, min(1, rho)) ** 3
 
         # ---- corrector :893-901
@@ -274,7 +294,8 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
                      r.w - eng.mul_G(dz.y),
                      r.v - (eng.mul_A(dz.y) - dz.s),
                      r.s - (pb1 + pb2))
-            rnorm = (nrm(rI.y) + nrm(rI.w) + mnrm(rI.v) + mnrm(rI.s)) / (n + 2 * m)
+            (ry2, rw2), (rv2, rs2) = dots(((rI.y, rI.y), (rI.w, rI.w)), ((rI.v, rI.v), (rI.s, rI.s)))
+            rnorm = (math.sqrt(ry2) + math.sqrt(rw2) + math.sqrt(rv2) + math.sqrt(rs2)) / (n + 2 * m_glob)
             if rnorm < refinementThreshold:
                 break
             dzr = solve(rI)
@@ -284,9 +305,8 @@ def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
             dz.s += dzr.s
 
         # ---- step :927-932
-        a_v = min(maxstep(z.v, dz.v, 1 - DTB), 1)
-        a_s = min(maxstep(z.s, dz.s, 1 - DTB), 1)
-        alpha = min(a_v, a_s)
+        a_v, a_s = maxstep2(z.v, dz.v, z.s, dz.s, 1 - DTB)
+        alpha = min(min(a_v, 1), min(a_s, 1))
         z.y = z.y - alpha * dz.y
         z.w = z.w - alpha * dz.w
         z.v = z.v - alpha * dz.v

@@ -90,7 +90,10 @@ def _gloo_worker(rank, world, port, q):
     red = TorchReducer()
     tot = red.sum(float(v[lo:hi] @ s[lo:hi]))
     mn = red.min(float(np.min(v[lo:hi])))
-    q.put((rank, float(np.abs(Hpart.numpy() - Hfull).max()), abs(tot - v @ s), abs(mn - v.min())))
+    tt = red.sum_tensor_(torch.tensor([float(v[lo:hi] @ s[lo:hi]), float(hi - lo)], dtype=torch.float64))
+    ml = red.min_list([float(np.min(v[lo:hi])), float(rank)])
+    ok = abs(float(tt[0]) - v @ s) < 1e-12 and float(tt[1]) == m and ml[0] == v.min() and ml[1] == 0.0
+    q.put((rank, float(np.abs(Hpart.numpy() - Hfull).max()), abs(tot - v @ s), abs(mn - v.min()) + (0.0 if ok else 1.0)))
     dist.destroy_process_group()
 
 
@@ -108,3 +111,41 @@ def test_sharded_gram_allreduce_world2_gloo():
         assert p.exitcode == 0
     for rank, dh, ds, dm in res:
         assert dh < 1e-12 and ds < 1e-12 and dm == 0.0
+
+
+def test_block_flatten_veccongurance():
+    R = np.arange(9.0).reshape(3, 3)
+    F = B.Block([B.Diagonal([1.0]), B.VecCongurance(R)])
+    kind, fa, fb, fD, fR = F.flatten()
+    assert kind.tolist() == [0, 2] and len(fa) == 1 + 6 and F.size == 7
+    assert np.array_equal(fR, R.ravel(order="F"))            # column-major, as Julia's vec(R)
+
+
+def test_julia_shim_binds_the_protocol_symbols():
+    """The ccall shim a ConicIP.jl maintainer adds must name the same C symbols the header declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "conicip.jl_b200", "julia", "ConicIPB200.jl")).read()
+    hdr = open(os.path.join(root, "include", "conicip_b200.h")).read()
+    used = set(re.findall(r"\(:(cip_[a-z_0-9]+), LIB\)", jl))
+    declared = set(re.findall(r"\b(cip_[a-z0-9_A-Z]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
+    assert used <= declared
+    for s in ("cip_create", "cip_destroy", "cip_factor", "cip_solve", "cip_last_error"):
+        assert s in used
+
+
+def test_bench_reference_arm_schema():
+    """`bench.py --impl reference` prints one JSON line with the contract's keys (tiny size here)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n", "256", "--m", "1024",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--no-solve", action="store_true", help="skip the full time-to-1e-8 solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--py-driver", action="store_true", help="also time the Python host driver (conicIP) on the solve")
     return ap.parse_args()
 
 
@@ -310,31 +311,38 @@ def run_b200(args, n, m):
                               "solve_each": st1["ms_solve"]},
     }
 
-    # ---- full interior-point solve: time-to-1e-8
+    # ---- full interior-point solve: time-to-1e-8 (native loop: one cip_ipm_solve call per rank)
     solve_info = None
     if not args.no_solve:
-        class _Shape:
-            def __init__(self, *s):
-                self.shape = s
-
-        def kk(Q, A, G, cd):
-            def gen(F, Finvt=None):
-                st = eng.factor_resident() if isinstance(F, cb.DeviceBlock) else eng.factor(F)
-                assert st == 0, st
-                return lambda y, w, v: eng.solve(y, w, v)
-            gen.engine = eng
-            return gen
-
         barrier()
         t0 = time.perf_counter()
-        sol = cb.conicIP(_Shape(n, n), c_vec.cpu().numpy(), _Shape(m_loc, n), b_loc.cpu().numpy(),
-                         [("R", m_loc)], kktsolver=kk, optTol=1e-8,
-                         reducer=TorchReducer() if world > 1 else None)
+        _, _, _, info = eng.ipm_solve(c_vec, b_loc, None, optTol=1e-8)
         barrier()
         t_solve = maxr(time.perf_counter() - t0)
-        solve_info = {"time_to_1e-8_s": t_solve, "status": sol.status, "iterations": sol.Iter,
-                      "factors": sol.factors, "solves": sol.solves, "prFeas": sol.prFeas,
-                      "duFeas": sol.duFeas, "muFeas": sol.muFeas}
+        solve_info = {"time_to_1e-8_s": t_solve, "status": info["status"], "iterations": info["Iter"],
+                      "factors": info["factors"], "solves": info["solves"], "prFeas": info["prFeas"],
+                      "duFeas": info["duFeas"], "muFeas": info["muFeas"], "driver": "cip_ipm_solve (native)"}
+        if args.py_driver:
+            class _Shape:
+                def __init__(self, *s):
+                    self.shape = s
+
+            def kk(Q, A, G, cd):
+                def gen(F, Finvt=None):
+                    st = eng.factor_resident() if isinstance(F, cb.DeviceBlock) else eng.factor(F)
+                    assert st == 0, st
+                    return lambda y, w, v: eng.solve(y, w, v)
+                gen.engine = eng
+                return gen
+
+            barrier()
+            t0 = time.perf_counter()
+            sol = cb.conicIP(_Shape(n, n), c_vec.cpu().numpy(), _Shape(m_loc, n), b_loc.cpu().numpy(),
+                             [("R", m_loc)], kktsolver=kk, optTol=1e-8,
+                             reducer=TorchReducer() if world > 1 else None)
+            barrier()
+            solve_info["python_driver"] = {"time_to_1e-8_s": maxr(time.perf_counter() - t0), "status": sol.status,
+                                           "iterations": sol.Iter, "factors": sol.factors, "solves": sol.solves}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

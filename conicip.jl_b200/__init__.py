@@ -14,7 +14,7 @@ from ._lib import (BLK_DIAG, BLK_VECCONG, BLK_WOODBURY, CONE_Q, CONE_R, CONE_S, 
 from .blocks import Block, DeviceBlock, Diagonal, SymWoodbury, VecCongurance  # noqa: F401
 from .engine import Engine, measure_fp64_peaks, nccl_unique_id  # noqa: F401
 from .kktsolver import kktsolver_b200, make_kktsolver  # noqa: F401
-from .driver import Solution, conicIP  # noqa: F401
+from .driver import Solution, conicIP, conicIP_native  # noqa: F401
 from . import problems, dist  # noqa: F401
 
 __version__ = "0.1.0"

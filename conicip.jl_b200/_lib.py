@@ -31,6 +31,21 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_size_t), ("kernel_launches", C.c_longlong)]
 
 
+class IpmOptions(C.Structure):
+    _fields_ = [("struct_size", C.c_int), ("maxIters", C.c_int), ("maxRefinementSteps", C.c_int), ("verbose", C.c_int),
+                ("optTol", C.c_double), ("DTB", C.c_double), ("infeasTol", C.c_double),
+                ("refinementThreshold", C.c_double)]
+
+
+class IpmResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("Iter", C.c_int), ("factors", C.c_int), ("solves", C.c_int),
+                ("Mu", C.c_double), ("prFeas", C.c_double), ("duFeas", C.c_double), ("muFeas", C.c_double),
+                ("pobj", C.c_double), ("dobj", C.c_double), ("seconds", C.c_double)]
+
+
+STATUS_NAMES = {0: "None", 1: "Optimal", 2: "Infeasible", 3: "Unbounded", 4: "Abandoned", 5: "Error"}
+
+
 class CipError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"conicip_b200 error {code}: {msg}")
@@ -62,6 +77,7 @@ SIGNATURES = {
     "cip_mul_A": (C.c_int, [C.c_void_p, C.c_int, _P, _P]),
     "cip_mul_G": (C.c_int, [C.c_void_p, C.c_int, _P, _P]),
     "cip_mul_Q": (C.c_int, [C.c_void_p, _P, _P]),
+    "cip_ipm_solve": (C.c_int, [C.c_void_p, _P, _P, _P, C.POINTER(IpmOptions), _P, _P, _P, C.POINTER(IpmResult)]),
     "cip_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cip_get_H": (C.c_int, [C.c_void_p, _P, C.c_int]),
     "cip_form_H": (C.c_int, [C.c_void_p]),

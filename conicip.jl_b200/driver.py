@@ -63,6 +63,22 @@ class LocalReducer:
         return list(xs)
 
 
+def conicIP_native(Q, c, A, b, cone_dims, G=None, d=None, *, engine=None, **opts):
+    """Same problem statement and options as `conicIP`, but the loop itself runs inside the library
+    (`cip_ipm_solve`): one C call per solve.  Pass `engine=` to reuse a handle."""
+    from .engine import Engine
+    eng = engine or Engine(Q, A, G if (G is not None and G.shape[0]) else None, cone_dims)
+    y, w, v, info = eng.ipm_solve(np.asarray(c, dtype=np.float64), np.asarray(b, dtype=np.float64),
+                                  None if d is None else np.asarray(d, dtype=np.float64), **opts)
+    sol = Solution(np.asarray(y), np.asarray(w), np.asarray(v), status=info["status"], Iter=info["Iter"],
+                   Mu=info["Mu"], prFeas=info["prFeas"], duFeas=info["duFeas"], muFeas=info["muFeas"],
+                   pobj=info["pobj"], dobj=info["dobj"], solves=info["solves"], factors=info["factors"])
+    sol.seconds = info["seconds"]
+    if engine is None:
+        eng.close()
+    return sol
+
+
 def conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, kktsolver=kktsolver_b200,
             optTol=1e-6, DTB=0.01, verbose=False, maxRefinementSteps=3, maxIters=100,
             infeasTol=None, refinementThreshold=None, reducer=None, global_cone_dims=None):

@@ -281,6 +281,28 @@ class Engine:
         check(lib().cip_mul_Q(self._h, self._ptr(x, self.n), self._ptr(y, self.n)))
         return y
 
+    # ------------------------------------------------------------------ native IP loop
+    def ipm_solve(self, c, b, d=None, *, optTol=1e-6, DTB=0.01, maxRefinementSteps=3, maxIters=100,
+                  infeasTol=None, refinementThreshold=None, verbose=False):
+        """`cip_ipm_solve`: the whole of `conicIP` (src/ConicIP.jl:468-939) behind one C call."""
+        from ._lib import IpmOptions, IpmResult, STATUS_NAMES
+        dev, (c, b, d) = self._prep(c, b, d if (d is not None and len(d)) else None)
+        o = IpmOptions()
+        o.struct_size = C.sizeof(IpmOptions)
+        o.maxIters, o.maxRefinementSteps, o.verbose = int(maxIters), int(maxRefinementSteps), int(verbose)
+        o.optTol, o.DTB = float(optTol), float(DTB)
+        o.infeasTol = -1.0 if infeasTol is None else float(infeasTol)
+        o.refinementThreshold = -1.0 if refinementThreshold is None else float(refinementThreshold)
+        y, w, v = self._new(dev, self.n), self._new(dev, self.p), self._new(dev, self.m)
+        r = IpmResult()
+        check(lib().cip_ipm_solve(self._h, self._ptr(c, self.n), self._ptr(b, self.m) if self.m else None,
+                                  self._ptr(d, self.p) if self.p else None, C.byref(o),
+                                  self._ptr(y, self.n), self._ptr(w, self.p) if self.p else None,
+                                  self._ptr(v, self.m) if self.m else None, C.byref(r)))
+        info = {k: getattr(r, k) for k, _ in IpmResult._fields_}
+        info["status"] = STATUS_NAMES[r.status]
+        return y, w, v, info
+
     # ------------------------------------------------------------------ multi-GPU / misc
     def comm_init(self, nranks, rank, unique_id):
         check(lib().cip_comm_init(self._h, nranks, rank, unique_id))

@@ -148,6 +148,35 @@ int cip_mul_A(cip_handle h, int trans, const double* x, double* y);
 int cip_mul_G(cip_handle h, int trans, const double* x, double* y);
 int cip_mul_Q(cip_handle h, const double* x, double* y);
 
+/* ---------------------------------------------------------------- device-resident IP loop
+ * SURVEY 8f rank 1 (no counterpart in the reference, whose loop runs in Julia): the whole of
+ * `conicIP` (src/ConicIP.jl:468-939: initial point :704-713, NT scaling, predictor :879-887,
+ * corrector :893-901, refinement :909-921, step :927-932, stopping / infeasibility tests
+ * :763-873) on device-resident vectors behind one call.  c (n), b (m: this rank's rows when
+ * sharded), d (p) in; y (n), w (p), v (m) out; host or device pointers. */
+#define CIP_STATUS_NONE       0
+#define CIP_STATUS_OPTIMAL    1
+#define CIP_STATUS_INFEASIBLE 2
+#define CIP_STATUS_UNBOUNDED  3
+#define CIP_STATUS_ABANDONED  4
+#define CIP_STATUS_ERROR      5
+typedef struct cip_ipm_options {
+  int    struct_size;
+  int    maxIters;              /* 100  (src/ConicIP.jl:504) */
+  int    maxRefinementSteps;    /* 3    (:503) */
+  int    verbose;
+  double optTol;                /* 1e-6 (:500) */
+  double DTB;                   /* 0.01 (:501) */
+  double infeasTol;             /* < 0: = optTol (:506) */
+  double refinementThreshold;   /* < 0: = optTol/1e7 (:509) */
+} cip_ipm_options;
+typedef struct cip_ipm_result {
+  int    status, Iter, factors, solves;
+  double Mu, prFeas, duFeas, muFeas, pobj, dobj, seconds;
+} cip_ipm_result;
+int cip_ipm_solve(cip_handle h, const double* c, const double* b, const double* d,
+                  const cip_ipm_options* opts, double* y, double* w, double* v, cip_ipm_result* result);
+
 /* ---------------------------------------------------------------- introspection */
 int cip_stats(cip_handle h, cip_stats_t* out);
 /* copy the current reduced matrix H (after cip_factor: its Cholesky factor L in the

@@ -1,0 +1,79 @@
+"""`cip_ipm_solve` (the native device-resident IP loop) against the oracle, the
+reference goldens and the Python host driver: same statuses, iteration counts and solutions."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conicip_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def native(prob, **kw):
+    import conicip_b200 as cb
+    opts = dict(optTol=prob.get("optTol", 1e-7))
+    opts.update(kw)
+    return cb.conicIP_native(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"], **opts)
+
+
+@pytest.mark.parametrize("name", ["sphere", "combined", "simplex", "soc_direct", "mixed"])
+def test_native_matches_golden_fixture(name):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_small.json")))["solves"][name]
+    s = native(getattr(P, name)(), optTol=g["optTol"])
+    assert s.status == g["status"] and abs(s.Iter - g["Iter"]) <= 1
+    assert rel(s.y, g["y"]) < 1e-6 and rel(s.v, g["v"]) < 1e-6
+    if len(g["w"]):
+        assert rel(s.w, g["w"]) < 1e-6
+    assert abs(s.Mu - g["Mu"]) <= 1e-5 * abs(g["Mu"])
+    assert max(s.prFeas, s.duFeas, s.muFeas) < g["optTol"]
+
+
+def test_native_reference_simplex_golden():
+    s = native(P.simplex(), optTol=1e-8)                                   # runtests.jl:235-240
+    assert s.status == "Optimal" and s.Iter == 11
+    assert abs(s.Mu - 2.7686402945528533e-9) <= 1e-7 * 2.7686402945528533e-9
+
+
+def test_native_equals_python_driver():
+    import conicip_b200 as cb
+    prob = P.config3(n=256, ncones=24, k=9, p=12, seed=9)
+    a = native(prob, optTol=1e-8)
+    b = cb.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"], optTol=1e-8)
+    assert a.status == b.status == "Optimal" and a.Iter == b.Iter
+    assert a.factors == b.factors and a.solves == b.solves
+    assert rel(a.y, b.y) < 1e-9 and rel(a.v, b.v) < 1e-9 and rel(a.w, b.w) < 1e-9
+
+
+def test_native_statuses():
+    assert native(P.simplex(), maxIters=2).status == "Abandoned"
+    assert native(P.infeasible()).status == "Infeasible"
+    s = native(P.unbounded())
+    assert s.status == "Unbounded" and np.all(np.isnan(s.v))
+    so = O.conicIP(P.unbounded()["Q"], P.unbounded()["c"], P.unbounded()["A"], P.unbounded()["b"],
+                   P.unbounded()["cone_dims"], optTol=1e-7, kktsolver=O.pivot(O.kktsolver_2x2))
+    assert rel(s.y, so.y) < 1e-6
+
+
+def test_native_sdp_projection():
+    c = O.vecm(np.diag([1.0, 1, 1, -1, -1, -1]))                            # runtests.jl:527-552
+    import conicip_b200 as cb
+    s = cb.conicIP_native(np.eye(21), c, np.eye(21), np.zeros(21), [("S", 21)], optTol=1e-7)
+    assert s.status == "Optimal" and abs(s.Iter - 6) <= 1
+    assert np.abs(O.mat(s.y) - np.diag([1.0, 1, 1, 0, 0, 0])).max() < 1e-3
+
+
+def test_native_config1_vs_oracle():
+    prob = P.config1()
+    s = native(prob)
+    so = O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], optTol=1e-8,
+                   kktsolver=O.pivot(O.kktsolver_2x2))
+    assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1
+    assert rel(s.y, so.y) < 1e-6 and rel(s.v, so.v) < 1e-6
+    assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8

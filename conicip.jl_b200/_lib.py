@@ -31,6 +31,11 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_size_t), ("kernel_launches", C.c_longlong)]
 
 
+class Csc(C.Structure):
+    _fields_ = [("nrows", C.c_int), ("ncols", C.c_int), ("colptr", C.c_void_p), ("rowval", C.c_void_p),
+                ("nzval", C.c_void_p), ("index_base", C.c_int)]
+
+
 class IpmOptions(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("maxIters", C.c_int), ("maxRefinementSteps", C.c_int), ("verbose", C.c_int),
                 ("optTol", C.c_double), ("DTB", C.c_double), ("infeasTol", C.c_double),
@@ -61,6 +66,8 @@ SIGNATURES = {
     "cip_version": (C.c_int, []),
     "cip_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int,
                              _P, C.c_int, C.c_int, _P, _P, C.POINTER(Options)]),
+    "cip_create_csc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Csc), C.POINTER(Csc), C.POINTER(Csc),
+                                 C.c_int, _P, _P, C.POINTER(Options)]),
     "cip_destroy": (C.c_int, [C.c_void_p]),
     "cip_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "cip_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),

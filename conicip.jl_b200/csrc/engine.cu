@@ -252,9 +252,36 @@ extern "C" {
 const char* cip_last_error(void) { return cip::g_err; }
 int cip_version(void) { return 100; }
 
-int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
-               const double* G, int ldg, int ncones, const int* cone_type, const int* cone_dim,
-               const cip_options* opts) {
+}  // extern "C"
+
+namespace {
+
+// upload a CSC matrix (host or device arrays) and scatter it into a zero-initialised Q4 buffer
+int upload_csc(cip_engine* h, double* dst, int ld, const cip_csc* M, int transpose) {
+  const long long ncols = M->ncols;
+  if (ncols == 0) return 0;
+  std::vector<long long> cp(2);
+  CIP_CUDA(cudaMemcpy(&cp[0], M->colptr, 8, cudaMemcpyDefault));
+  CIP_CUDA(cudaMemcpy(&cp[1], M->colptr + ncols, 8, cudaMemcpyDefault));
+  const long long nnz = cp[1] - cp[0];
+  if (nnz <= 0) return 0;
+  long long *dcp = nullptr, *drv = nullptr;
+  double* dnz = nullptr;
+  CIP_CUDA(cudaMalloc(&dcp, (ncols + 1) * 8));
+  CIP_CUDA(cudaMalloc(&drv, nnz * 8));
+  CIP_CUDA(cudaMalloc(&dnz, nnz * 8));
+  CIP_CUDA(cudaMemcpyAsync(dcp, M->colptr, (ncols + 1) * 8, cudaMemcpyDefault, h->stream));
+  CIP_CUDA(cudaMemcpyAsync(drv, M->rowval, nnz * 8, cudaMemcpyDefault, h->stream));
+  CIP_CUDA(cudaMemcpyAsync(dnz, M->nzval, nnz * 8, cudaMemcpyDefault, h->stream));
+  int rc = scatter_csc_q4(dst, ld, (int)ncols, dcp, drv, dnz, M->index_base, transpose, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(dcp); cudaFree(drv); cudaFree(dnz);
+  return rc;
+}
+
+int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs, int ncones,
+                const int* cone_type, const int* cone_dim, const cip_options* opts) {
   if (!out || n <= 0 || m < 0 || p < 0 || ncones < 0) {
     set_error("cip_create: bad dimensions n=%d m=%d p=%d ncones=%d", n, m, p, ncones);
     return -1;
@@ -371,7 +398,9 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
   cudaStream_t s = h->stream;
 
   // Q
-  if (h->opt.q_kind == 0) {
+  if (Qs) {
+    CIP_TRY(upload_csc(h, h->Qq4, h->n_pad, Qs, 0));
+  } else if (h->opt.q_kind == 0) {
     if (!Q) { set_error("Q is null"); return -1; }
     if (is_device_ptr(Q)) {
       CIP_TRY(pack_rows_q4(h->Qq4, h->n_pad, Q, ldq, n, n, h->n_pad, h->n_pad, s));
@@ -404,8 +433,10 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
 
   // A (transposed into Q4: rows = columns of A)
   if (m > 0) {
-    if (!A) { set_error("A is null"); return -1; }
-    if (is_device_ptr(A)) {
+    if (!A && !As) { set_error("A is null"); return -1; }
+    if (As) {
+      CIP_TRY(upload_csc(h, h->At4, h->n_pad, As, 1));
+    } else if (is_device_ptr(A)) {
       CIP_TRY(pack_trans_q4(h->At4, h->n_pad, 0, A, lda, m, h->m_pad, n, s));
     } else {
       const int chunk = std::max(1, std::min(n, (int)((512u << 20) / ((size_t)m * 8))));
@@ -426,25 +457,29 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
 
   // G
   if (p > 0) {
-    if (!G) { set_error("G is null"); return -1; }
+    if (!G && !Gs) { set_error("G is null"); return -1; }
     const size_t pn = (size_t)h->p_pad * h->n_pad;
     CIP_TRY(dev_alloc(h, &h->G4, pn));
     CIP_TRY(dev_alloc(h, &h->Z4, pn));
     CIP_TRY(dev_alloc(h, &h->S4, (size_t)h->p_pad * h->p_pad));
     CIP_TRY(dev_alloc(h, &h->Sbase4, (size_t)h->p_pad * h->p_pad));
     CIP_TRY(dev_alloc(h, &h->WinvS, (size_t)h->p_pad * TILE));
-    double* stg = nullptr;
-    const double* gsrc = G;
-    int gld = ldg;
-    if (!is_device_ptr(G)) {
-      CIP_CUDA(cudaMalloc(&stg, (size_t)p * n * 8));
-      CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)p * 8, G, (size_t)ldg * 8, (size_t)p * 8, n, cudaMemcpyHostToDevice, s));
-      gsrc = stg;
-      gld = p;
+    if (Gs) {
+      CIP_TRY(upload_csc(h, h->G4, h->p_pad, Gs, 0));
+    } else {
+      double* stg = nullptr;
+      const double* gsrc = G;
+      int gld = ldg;
+      if (!is_device_ptr(G)) {
+        CIP_CUDA(cudaMalloc(&stg, (size_t)p * n * 8));
+        CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)p * 8, G, (size_t)ldg * 8, (size_t)p * 8, n, cudaMemcpyHostToDevice, s));
+        gsrc = stg;
+        gld = p;
+      }
+      CIP_TRY(pack_rows_q4(h->G4, h->p_pad, gsrc, gld, p, n, h->p_pad, h->n_pad, s));
+      CIP_CUDA(cudaStreamSynchronize(s));
+      if (stg) cudaFree(stg);
     }
-    CIP_TRY(pack_rows_q4(h->G4, h->p_pad, gsrc, gld, p, n, h->p_pad, h->n_pad, s));
-    CIP_CUDA(cudaStreamSynchronize(s));
-    if (stg) cudaFree(stg);
     CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, p, h->p_pad, 1.0, 1, s));
     if (h->opt.reg_eps_G != 0.0) CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, 0, p, h->opt.reg_eps_G, 1, s));
     CIP_TRY(make_q4_tensor_map(&h->mapZ.map, h->Z4, h->p_pad, h->n_pad / 4));
@@ -462,6 +497,33 @@ int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, c
   h->st.n = n; h->st.m = m; h->st.p = p; h->st.n_pad = h->n_pad; h->st.m_pad = h->m_pad; h->st.p_pad = h->p_pad;
   *out = h;
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+               const double* G, int ldg, int ncones, const int* cone_type, const int* cone_dim,
+               const cip_options* opts) {
+  return create_impl(out, n, m, p, Q, ldq, A, lda, G, ldg, nullptr, nullptr, nullptr, ncones, cone_type, cone_dim,
+                     opts);
+}
+
+int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, const cip_csc* G, int ncones,
+                   const int* cone_type, const int* cone_dim, const cip_options* opts) {
+  if (!A || A->ncols != n || (Q && (Q->nrows != n || Q->ncols != n)) || (G && G->nrows > 0 && G->ncols != n)) {
+    set_error("cip_create_csc: inconsistent matrix shapes");
+    return -1;
+  }
+  cip_options o{};
+  if (opts) memcpy(&o, opts, std::min<size_t>(sizeof(o), (size_t)opts->struct_size));
+  else o.device = -1;
+  o.struct_size = sizeof(o);
+  o.q_kind = 2;                         // Q comes from the CSC arrays (or is zero when Q == NULL)
+  const int p = G ? G->nrows : 0;
+  return create_impl(out, n, A->nrows, p, nullptr, 0, nullptr, 0, nullptr, 0, Q, A, (p > 0) ? G : nullptr, ncones,
+                     cone_type, cone_dim, &o);
 }
 
 int cip_destroy(cip_handle h) {

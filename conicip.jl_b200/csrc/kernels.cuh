@@ -17,6 +17,9 @@ int pack_trans_q4(double* dst, int ld, int r0, const double* src, int lds, int K
 int unpack_rows_q4(double* dst, int ldd, const double* src, int ld, int R, int K, cudaStream_t s);
 int add_diag_q4(double* X, int ld, int from, int to, double val, int set, cudaStream_t s);
 int set_diag_vec_q4(double* X, int ld, int n, const double* v, cudaStream_t s);
+// device CSC arrays (colptr[ncols+1], rowval/nzval[nnz], index base 0 or 1) scattered into a zeroed Q4 matrix
+int scatter_csc_q4(double* dst, int ld, int ncols, const long long* colptr, const long long* rowval,
+                   const double* nzval, int base, int transpose, cudaStream_t s);
 int fill_zero(double* p, size_t n, cudaStream_t s);
 
 // ---------------------------------------------------------------- mat-vec on Q4 (matvec.cu)

@@ -70,6 +70,20 @@ __global__ void set_diag_vec_kernel(double* X, int ld, int n, const double* __re
   if (i < n) X[q4_index(i, i, ld)] = v[i];
 }
 
+// CSC scatter: one CTA per column j; entry (i, j, val) goes to X[r=i,k=j] (transpose=0: Q, G) or
+// X[r=j,k=i] (transpose=1: A).  atomicAdd so duplicate entries sum, as in Julia's sparse().
+__global__ void scatter_csc_kernel(double* __restrict__ dst, int ld, const long long* __restrict__ colptr,
+                                   const long long* __restrict__ rowval, const double* __restrict__ nzval,
+                                   int base, int transpose) {
+  const int j = blockIdx.x;
+  const long long e0 = colptr[j] - base, e1 = colptr[j + 1] - base;
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const int i = (int)(rowval[e] - base);
+    const size_t idx = transpose ? q4_index(j, i, ld) : q4_index(i, j, ld);
+    atomicAdd(dst + idx, nzval[e]);
+  }
+}
+
 // out-partials[split][r] = sum over this split's k-quads of X[r, k] v[k]
 __global__ void __launch_bounds__(128)
 mv_rows_kernel(double* __restrict__ partial, const double* __restrict__ X, int ld, int R, int Kq,
@@ -191,6 +205,14 @@ int add_diag_q4(double* X, int ld, int from, int to, double val, int set, cudaSt
 int set_diag_vec_q4(double* X, int ld, int n, const double* v, cudaStream_t s) {
   if (n <= 0) return 0;
   set_diag_vec_kernel<<<(n + 127) / 128, 128, 0, s>>>(X, ld, n, v);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+int scatter_csc_q4(double* dst, int ld, int ncols, const long long* colptr, const long long* rowval,
+                   const double* nzval, int base, int transpose, cudaStream_t s) {
+  if (ncols <= 0) return 0;
+  scatter_csc_kernel<<<ncols, 128, 0, s>>>(dst, ld, colptr, rowval, nzval, base, transpose);
   CIP_CHECK_LAUNCH();
   return 0;
 }

@@ -50,6 +50,13 @@ class Engine:
         opts.reg_delta = reg_delta
         opts.reg_eps_G = reg_eps_G
         opts.q_kind = 0
+        self._torch = None
+        self._use_torch_stream = use_torch_stream
+        self.last_factor_status = 0
+
+        if not _is_torch(A) and sp.issparse(A):
+            self._create_csc(Q, A, G, opts)
+            return
 
         # ---- Q: dense, sparse, diagonal vector ("Id(n)", src/ConicIP.jl:18) or None (zero)
         if Q is None:
@@ -107,9 +114,41 @@ class Engine:
                           C.byref(opts))
         if rc != 0:
             raise _lib.CipError(rc, _lib.last_error())
-        self._torch = None
-        self._use_torch_stream = use_torch_stream
-        self.last_factor_status = 0
+
+    def _create_csc(self, Q, A, G, opts):
+        """Sparse LEVEL 1 (`cip_create_csc`): CSC arrays go to the device as they are, no dense copy."""
+        from ._lib import Csc
+        keep = []
+
+        def csc(M):
+            if M is None:
+                return None
+            M = sp.csc_matrix(M, dtype=np.float64)
+            M.sum_duplicates()
+            cp = np.ascontiguousarray(M.indptr, dtype=np.int64)
+            rv = np.ascontiguousarray(M.indices, dtype=np.int64)
+            nz = np.ascontiguousarray(M.data, dtype=np.float64)
+            keep.extend([cp, rv, nz])
+            s = Csc(M.shape[0], M.shape[1], cp.ctypes.data, rv.ctypes.data, nz.ctypes.data, 0)
+            keep.append(s)
+            return s
+
+        m, n = A.shape
+        if Q is not None and Q.shape != (n, n):
+            raise ValueError("Inconsistency in inequalities/objective")
+        if int(self.cone_off[-1]) != m:
+            raise ValueError("cone_dims do not cover the rows of A")
+        p = 0 if G is None else G.shape[0]
+        if p and G.shape[1] != n:
+            raise ValueError("Inconsistency in equalities/objective")
+        qs, as_, gs = csc(Q), csc(A), (csc(G) if p else None)
+        self.n, self.m, self.p = int(n), int(m), int(p)
+        self._h = C.c_void_p()
+        rc = lib().cip_create_csc(C.byref(self._h), self.n, C.byref(qs) if qs is not None else None, C.byref(as_),
+                                  C.byref(gs) if gs is not None else None, len(self.cone_dims),
+                                  self.cone_type.ctypes.data, self.cone_dim.ctypes.data, C.byref(opts))
+        if rc != 0:
+            raise _lib.CipError(rc, _lib.last_error())
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

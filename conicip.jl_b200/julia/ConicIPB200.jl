@@ -36,11 +36,37 @@ function check(rc::Cint)
     return rc
 end
 
+struct Csc                # mirrors cip_csc: a SparseMatrixCSC{Float64,Int64} passed field by field
+    nrows::Cint
+    ncols::Cint
+    colptr::Ptr{Int64}
+    rowval::Ptr{Int64}
+    nzval::Ptr{Cdouble}
+    index_base::Cint
+end
+Csc(M::SparseMatrixCSC{Float64,Int64}) = Csc(size(M, 1), size(M, 2), pointer(M.colptr), pointer(M.rowval), pointer(M.nzval), 1)
+
 mutable struct Engine
     h::Ptr{Cvoid}
     n::Int; m::Int; p::Int
     function Engine(Q, A, G, cone_dims; reg_delta = 0.0)
         n = size(Q, 1); m = size(A, 1); p = size(G, 1)
+        if A isa SparseMatrixCSC          # sparse LEVEL 1: no dense copy on the host (cip_create_csc)
+            Qs = SparseMatrixCSC{Float64,Int64}(sparse(Q)); As = SparseMatrixCSC{Float64,Int64}(A)
+            Gs = SparseMatrixCSC{Float64,Int64}(sparse(G))
+            ct = Cint[CONE_CODE[t] for (t, _) in cone_dims]; cdim = Cint[k for (_, k) in cone_dims]
+            opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, Cint(2), Cint(0)))
+            hp = Ref{Ptr{Cvoid}}(C_NULL)
+            GC.@preserve Qs As Gs begin
+                rc = ccall((:cip_create_csc, LIB), Cint,
+                           (Ref{Ptr{Cvoid}}, Cint, Ref{Csc}, Ref{Csc}, Ref{Csc}, Cint, Ptr{Cint}, Ptr{Cint}, Ref{Options}),
+                           hp, n, Ref(Csc(Qs)), Ref(Csc(As)), Ref(Csc(Gs)), length(ct), ct, cdim, opts)
+            end
+            rc != 0 && error("cip_create_csc: ", lasterr())
+            e = new(hp[], n, m, p)
+            finalizer(x -> ccall((:cip_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
+            return e
+        end
         # Julia arrays are column-major: dense copies are passed as they are (SURVEY 8b "Argument types")
         Qd = Q isa Diagonal ? collect(Q.diag) : Matrix{Float64}(Q)
         qk = Q isa Diagonal ? Cint(1) : Cint(0)
@@ -135,6 +161,36 @@ cone_prod!(eng::Engine, o, x, y) = check(ccall((:cip_cone_prod, LIB), Cint,
     (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), eng.h, x, y, o))
 cone_div!(eng::Engine, o, x, y) = check(ccall((:cip_cone_div, LIB), Cint,
     (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), eng.h, x, y, o))
+
+# ---- the whole solve behind one ccall (cip_ipm_solve; SURVEY 8f rank 1): same arguments, options
+# and `Solution` as `ConicIP.conicIP`, with the loop of src/ConicIP.jl:468-939 running in the library
+# on device-resident vectors.
+struct IpmOptions
+    struct_size::Cint; maxIters::Cint; maxRefinementSteps::Cint; verbose::Cint
+    optTol::Cdouble; DTB::Cdouble; infeasTol::Cdouble; refinementThreshold::Cdouble
+end
+struct IpmResult
+    status::Cint; Iter::Cint; factors::Cint; solves::Cint
+    Mu::Cdouble; prFeas::Cdouble; duFeas::Cdouble; muFeas::Cdouble; pobj::Cdouble; dobj::Cdouble; seconds::Cdouble
+end
+const STATUS = (:None, :Optimal, :Infeasible, :Unbounded, :Abandoned, :Error)
+
+function conicIP_b200(Q, c::AbstractVector, A, b::AbstractVector, cone_dims,
+                      G = spzeros(0, length(c)), d = zeros(0);
+                      optTol = 1e-6, DTB = 0.01, verbose = false, maxRefinementSteps = 3, maxIters = 100,
+                      infeasTol = optTol, refinementThreshold = optTol / 1e7)
+    eng = Engine(Q, A, G, cone_dims)
+    y = Vector{Float64}(undef, eng.n); w = Vector{Float64}(undef, eng.p); v = Vector{Float64}(undef, eng.m)
+    opts = Ref(IpmOptions(Cint(sizeof(IpmOptions)), maxIters, maxRefinementSteps, verbose, optTol, DTB, infeasTol,
+                          refinementThreshold))
+    res = Ref(IpmResult(0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0))
+    check(ccall((:cip_ipm_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{IpmOptions}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ref{IpmResult}),
+                eng.h, Vector{Float64}(c), Vector{Float64}(b), Vector{Float64}(d), opts, y, w, v, res))
+    r = res[]
+    return ConicIP.Solution(y, w, v, STATUS[r.status + 1], r.Iter, r.Mu, r.prFeas, r.duFeas, r.muFeas, r.pobj, r.dobj)
+end
 
 # ---- MOI: `ConicIP.Optimizer` has no kktsolver field (src/MOI_wrapper.jl:19-31) and optimize!
 # forwards only verbose/optTol/maxIters (:278-282).  The one-field extension a maintainer adds:

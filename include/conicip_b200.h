@@ -83,6 +83,20 @@ int cip_create(cip_handle* out, int n, int m, int p,
                const double* G, int ldg,
                int ncones, const int* cone_type, const int* cone_dim,
                const cip_options* opts);
+/* LEVEL 1 from sparse inputs: Julia's `SparseMatrixCSC{Float64,Int64}` fields
+ * (.colptr, .rowval, .nzval; index_base = 1) are passed as they are -- `A`, `G` and `Q` reach conicIP
+ * sparse from the MOI wrapper (src/MOI_wrapper.jl:152-275) and from the README example -- and are
+ * expanded into the device layout by a scatter kernel, with no dense copy on the host.
+ * Q == NULL means Q = 0; G == NULL or G->nrows == 0 means no equality block. */
+typedef struct cip_csc {
+  int nrows, ncols;
+  const int64_t* colptr;   /* ncols + 1 */
+  const int64_t* rowval;   /* nnz */
+  const double*  nzval;    /* nnz */
+  int index_base;          /* 1 for Julia, 0 for C / SciPy */
+} cip_csc;
+int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, const cip_csc* G,
+                   int ncones, const int* cone_type, const int* cone_dim, const cip_options* opts);
 int cip_destroy(cip_handle h);
 
 /* Row-sharded multi-GPU (no counterpart in the reference): one

@@ -62,3 +62,59 @@ def test_c2_full_solve_to_1e8():
     assert slack.min() > -1e-7 and s.v.min() > -1e-12
     assert np.linalg.norm(Q @ s.y - c - A.T @ s.v) <= 1e-7 * (1 + np.linalg.norm(c))
     assert abs(slack @ s.v) / len(b) < 1e-7
+
+
+def test_c4_headline_size_properties():
+    """The bench configuration itself (C4: n=16384, m=262144, 73 GB resident): the oracle cannot run
+    at this size, so the SYRK + Cholesky + sweeps are cross-checked against independent kernels and
+    a float64 host evaluation: (1) sampled entries of H, (2) H dy = rhs through the mat-vec kernels,
+    (3) the 3x3 system residual, (4) linearity."""
+    import torch
+    import scipy.sparse as sp
+    import conicip_b200 as cb
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120e9:
+        pytest.skip("needs ~110 GB of free device memory")
+    prob = P.config4_device()
+    n, m = prob["n"], prob["m"]
+    At = prob["At"]
+    qd = prob["qdiag"].cpu().numpy()
+    eng = cb.Engine(sp.diags(qd).tocsr(), At.t(), None, prob["cone_dims"])
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    v = torch.rand(m, generator=g, dtype=torch.float64, device="cuda") * 1e3 + 1e-3
+    s = torch.rand(m, generator=g, dtype=torch.float64, device="cuda") * 1e3 + 1e-3
+    eng.nt_scaling(v, s)
+    eng.form_H()
+    dsc = (v / s)                                                         # W^-2
+    # (1) sampled entries (lower triangle) against a float64 evaluation of Q_ij + sum_k d_k A_ki A_kj
+    cols = [0, 1, 127, 128, 5000, 16383]
+    Hs = {}
+    H = None
+    rows = torch.stack([At[c] for c in cols])                             # (6, m) = columns of A
+    ref = (rows * dsc) @ rows.t()
+    ref += torch.diag(torch.as_tensor(qd[cols], device="cuda"))
+    Hfull = eng.get_H()
+    for a, i in enumerate(cols):
+        for b_, j in enumerate(cols):
+            if i >= j:
+                assert abs(Hfull[i, j] - float(ref[a, b_])) <= 1e-11 * (abs(float(ref[a, b_])) + float(ref[a, a] * ref[b_, b_]) ** 0.5 * 1e-3)
+    del Hfull, At
+    prob.pop("At")
+    torch.cuda.empty_cache()
+    assert eng.factor_H() == 0
+    ry = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
+    rv = torch.randn(m, generator=g, dtype=torch.float64, device="cuda")
+    dy, _, dv = eng.solve(ry, None, rv)
+    # (2) reduced system through the mat-vec kernels: (Q + A' D A) dy = ry + A' D rv
+    Hdy = eng.mul_Q(dy) + eng.mul_A(eng.mul_A(dy) * dsc, trans=True)
+    rhs = ry + eng.mul_A(rv * dsc, trans=True)
+    assert float(torch.linalg.vector_norm(Hdy - rhs) / torch.linalg.vector_norm(rhs)) < 1e-11
+    # (3) 3x3 system rows 1 and 3
+    r1 = eng.mul_Q(dy) - eng.mul_A(dv, trans=True) - ry
+    r3 = eng.mul_A(dy) + dv / dsc - rv
+    assert float(torch.linalg.vector_norm(r1) / torch.linalg.vector_norm(ry)) < 1e-9
+    assert float(torch.linalg.vector_norm(r3) / torch.linalg.vector_norm(rv)) < 1e-9
+    # (4) exact linearity under scaling by 2
+    dy2, _, dv2 = eng.solve(2.0 * ry, None, 2.0 * rv)
+    assert torch.equal(dy2, 2.0 * dy) and torch.equal(dv2, 2.0 * dv)
+    eng.close()

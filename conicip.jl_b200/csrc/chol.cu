@@ -4,6 +4,7 @@
 //                        A22 -= L21 * L21'           -> gemm_nt (lower, same tiles as the SYRK)
 // Replaces LAPACK qr/lu at src/kktsolvers.jl:35,:295 and the solves at :39-48,:299.
 #include "kernels.cuh"
+#include "nccl_dl.h"
 
 namespace cip {
 
@@ -432,6 +433,104 @@ int chol_factor(const CholPlan& p, cudaStream_t s) {
   }
   CIP_CUDA(cudaEventRecord(p.evS, sc));
   CIP_CUDA(cudaStreamWaitEvent(s, p.evS, 0));
+  return 0;
+}
+
+// ---------------------------------------------------------------- distributed (block-cyclic) variant
+namespace {
+// inner factorisation of outer panel [J0, J1) on stream sc (the same sequence chol_factor uses)
+int factor_outer_panel(const CholPlan& p, int J0, int J1, cudaStream_t sc, int smem) {
+  const int np = p.npanels;
+  for (int jb = J0; jb < J1; ++jb) {
+    const int j0 = jb * NB;
+    potrf_diag_kernel<<<1, 512, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
+    CIP_CHECK_LAUNCH();
+    const int rem = np - jb - 1;
+    if (rem == 0) break;
+    GemmArgs t{};
+    t.lower = 0; t.ntm = rem; t.ntn = 1; t.sym = 0;
+    t.x_row0 = j0 + NB; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = NB / 32;
+    t.Cin = nullptr; t.Cout = p.H; t.ldc = p.ld; t.c_row0 = j0 + NB; t.c_col0 = j0; t.alpha = 1.0;
+    CIP_TRY(launch_gemm_nt(p.mapH, p.mapWinv, t, sc));
+    const int inner_cols = J1 - jb - 1;
+    if (inner_cols > 0) {
+      GemmArgs c{};
+      c.lower = 0; c.ntm = rem; c.ntn = inner_cols; c.sym = 0;
+      c.x_row0 = j0 + NB; c.y_row0 = j0 + NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
+      c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + NB; c.c_col0 = j0 + NB; c.alpha = -1.0;
+      CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
+    }
+  }
+  return 0;
+}
+// C[rows >= first row of outer panel Jc, columns of Jc] -= L[rows, panel J] * L[cols of Jc, panel J]'
+int update_outer_panel(const CholPlan& p, int OUTER, int J, int Jc, cudaStream_t st) {
+  const int np = p.npanels;
+  const int J0 = J * OUTER, J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
+  const int C0 = Jc * OUTER, C1 = (C0 + OUTER < np) ? C0 + OUTER : np;
+  GemmArgs c{};
+  c.lower = 0; c.ntm = np - C0; c.ntn = C1 - C0; c.sym = 0;
+  c.x_row0 = C0 * NB; c.y_row0 = C0 * NB; c.x_kq0 = J0 * NB / 4; c.y_kq0 = J0 * NB / 4; c.nk = (J1 - J0) * NB / 32;
+  c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = C0 * NB; c.c_col0 = C0 * NB; c.alpha = -1.0;
+  return launch_gemm_nt(p.mapH, p.mapH, c, st);
+}
+}  // namespace
+
+int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
+  constexpr int OUTER = 4;
+  const NcclApi* api = nccl_api();
+  if (!api) return -1;
+  const int smem = (NB * SLD + 3 * NB + SB * PLD) * (int)sizeof(double);
+  if (!g_potrf_attr) {
+    CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    g_potrf_attr = true;
+  }
+  cudaStream_t sc = p.sc;
+  const int np = p.npanels, NO = (np + OUTER - 1) / OUTER, N = d.nranks, me = d.rank;
+  CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));
+  CIP_CUDA(cudaEventRecord(p.evS, s));
+  CIP_CUDA(cudaStreamWaitEvent(sc, p.evS, 0));
+  int myNext = me;                          // the next outer panel this rank will factor; its updates run on sc
+  for (int J = 0; J < NO; ++J) {
+    const int owner = J % N;
+    const int J0 = J * OUTER, J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
+    if (owner == me) CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem));
+    // broadcast the factored block column (all rows: one contiguous Q4 region) and its inverse blocks
+    {
+      double* panel = p.H + (size_t)(J0 * NB / 4) * p.ld * 4;
+      const size_t cnt = (size_t)(J1 - J0) * NB * p.ld;
+      int r = api->Broadcast(panel, panel, cnt, kNcclFloat64, owner, d.comm, sc);
+      if (r == 0) {
+        double* w = p.Winv + (size_t)J0 * NB * NB;
+        r = api->Broadcast(w, w, (size_t)(J1 - J0) * NB * NB, kNcclFloat64, owner, d.comm, sc);
+      }
+      if (r != 0) {
+        set_error("ncclBroadcast failed in the distributed Cholesky: %s", api->GetErrorString(r));
+        return -1;
+      }
+    }
+    CIP_CUDA(cudaEventRecord(p.evT[J & 1], sc));
+    if (owner == me) {
+      myNext += N;
+      // the new "next" panel has so far been updated on s: order sc after everything s has queued
+      CIP_CUDA(cudaEventRecord(p.evR[0], s));
+      CIP_CUDA(cudaStreamWaitEvent(sc, p.evR[0], 0));
+    }
+    if (myNext < NO && myNext > J) CIP_TRY(update_outer_panel(p, OUTER, J, myNext, sc));
+    CIP_CUDA(cudaStreamWaitEvent(s, p.evT[J & 1], 0));
+    for (int Jc = me; Jc < NO; Jc += N) {   // owned panels right of J, except the look-ahead one
+      if (Jc <= J || Jc == myNext) continue;
+      CIP_TRY(update_outer_panel(p, OUTER, J, Jc, s));
+    }
+  }
+  CIP_CUDA(cudaEventRecord(p.evS, sc));
+  CIP_CUDA(cudaStreamWaitEvent(s, p.evS, 0));
+  // a failed pivot is only known to the owner of that panel
+  int r = api->AllReduce(p.info, p.info, 1, kNcclInt32, kNcclMax, d.comm, s);
+  if (r != 0) {
+    set_error("ncclAllReduce(info) failed: %s", api->GetErrorString(r));
+    return -1;
+  }
   return 0;
 }
 

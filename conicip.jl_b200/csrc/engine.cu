@@ -7,6 +7,7 @@
 //                         -> Schur complement on G (same DMMA tiles).
 // LEVEL 3 (cip_solve)   : the pivot algebra of src/kktsolvers.jl:324-332 on the resident data.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -187,7 +188,22 @@ int form_H(cip_engine* h) {
 
 int factor_H(cip_engine* h) {
   cudaStream_t s = h->stream;
-  CIP_TRY(chol_factor(h->cholH, s));
+  // block-cyclic distributed factorisation when A is row-sharded (every rank holds the reduced H);
+  // opts.dist_chol: 0 = replicated, 1 = distributed, -1/unset = distributed iff >= 2 outer panels per rank
+  bool dist = false;
+  if (h->comm && h->nranks > 1) {
+    const int outer_panels = (h->cholH.npanels + 3) / 4;
+    int mode = h->opt.dist_chol;
+    if (const char* env = getenv("CIP_DIST_CHOL")) mode = atoi(env);
+    dist = (mode == 1) || (mode != 0 && outer_panels >= 2 * h->nranks);
+  }
+  if (dist) {
+    CholDist d;
+    d.nranks = h->nranks; d.rank = h->rank; d.comm = h->comm;
+    CIP_TRY(chol_factor_dist(h->cholH, s, d));
+  } else {
+    CIP_TRY(chol_factor(h->cholH, s));
+  }
   CIP_CUDA(cudaEventRecord(h->ev[4], s));
   if (h->p > 0) {
     // Z = G L^-T by a right-looking blocked substitution on the DMMA tiles, S = Z Z', S = Ls Ls'
@@ -288,6 +304,7 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
   }
   cip_engine* h = new cip_engine();
   *out = nullptr;
+  h->opt.dist_chol = -1;
   if (opts) memcpy(&h->opt, opts, std::min<size_t>(sizeof(cip_options), (size_t)opts->struct_size));
   else h->opt.device = -1;
   if (h->opt.device < 0) CIP_CUDA(cudaGetDevice(&h->device));
@@ -517,6 +534,7 @@ int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, c
     return -1;
   }
   cip_options o{};
+  o.dist_chol = -1;
   if (opts) memcpy(&o, opts, std::min<size_t>(sizeof(o), (size_t)opts->struct_size));
   else o.device = -1;
   o.struct_size = sizeof(o);

@@ -99,6 +99,14 @@ struct CholPlan {
 int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info);
 void chol_free_plan(CholPlan* p);
 int chol_factor(const CholPlan& p, cudaStream_t s);
+// Block-cyclic distributed variant: every rank holds the full matrix buffer, outer
+// panel J is factored by rank J % nranks and broadcast (NCCL), each rank applies it only to the outer
+// panels it owns.  On return every rank holds the complete factor L and all inv(L_jj) blocks.
+struct CholDist {
+  int nranks = 1, rank = 0;
+  void* comm = nullptr;   // ncclComm_t
+};
+int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d);
 // b (length n_pad) is overwritten with work; y receives the solution of L y = b
 int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s);
 // y is overwritten with work; x receives the solution of L' x = y

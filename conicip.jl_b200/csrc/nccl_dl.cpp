@@ -23,6 +23,7 @@ const NcclApi* nccl_api() {
   CIP_SYM(GetUniqueId, "ncclGetUniqueId")
   CIP_SYM(CommInitRank, "ncclCommInitRank")
   CIP_SYM(AllReduce, "ncclAllReduce")
+  CIP_SYM(Broadcast, "ncclBroadcast")
   CIP_SYM(CommDestroy, "ncclCommDestroy")
   CIP_SYM(GetErrorString, "ncclGetErrorString")
 #undef CIP_SYM

@@ -17,6 +17,8 @@ struct NcclApi {
   int (*CommInitRank)(void** comm, int nranks, NcclId id, int rank) = nullptr;
   int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm,
                    cudaStream_t stream) = nullptr;
+  int (*Broadcast)(const void* send, void* recv, size_t count, int dtype, int root, void* comm,
+                   cudaStream_t stream) = nullptr;
   int (*CommDestroy)(void* comm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -24,7 +26,9 @@ struct NcclApi {
 // returns nullptr (and sets the error string) if libnccl cannot be loaded
 const NcclApi* nccl_api();
 
+constexpr int kNcclInt32 = 2;
 constexpr int kNcclFloat64 = 8;
 constexpr int kNcclSum = 0;
+constexpr int kNcclMax = 2;
 
 }  // namespace cip

@@ -56,6 +56,7 @@ typedef struct cip_options {
   double reg_eps_G;     /* regularisation of the Schur complement S (default 0)           */
   int    q_kind;        /* 0 dense n*n (ldq), 1 diagonal (Q points to n doubles), 2 zero  */
   int    verbose;
+  int    dist_chol;     /* sharded handles: 0 replicated Cholesky, 1 block-cyclic distributed, -1 auto */
 } cip_options;
 
 typedef struct cip_stats_t {

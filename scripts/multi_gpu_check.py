@@ -24,7 +24,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     worst = 0.0
-    for prob in (P.mixed(n=200, mr=400, ncones=12, k=33, p=7, seed=21), P.mixed(n=300, mr=2000, ncones=0, k=3, p=0, seed=22)):
+    cases = [(P.mixed(n=200, mr=400, ncones=12, k=33, p=7, seed=21), -1),
+             (P.mixed(n=300, mr=2000, ncones=0, k=3, p=0, seed=22), -1),
+             # several 512-column outer panels: exercises the block-cyclic distributed Cholesky
+             (P.mixed(n=1700, mr=2600, ncones=4, k=17, p=9, seed=23), 1),
+             (P.mixed(n=1700, mr=2600, ncones=4, k=17, p=9, seed=23), 0)]
+    for prob, dist_chol in cases:
         Q, A, G, cd = prob["Q"], prob["A"], prob["G"], prob["cone_dims"]
         n, m, p = len(prob["c"]), A.shape[0], G.shape[0]
         lo, hi, lcd = shard_cones(cd, world)[rank]
@@ -45,7 +50,7 @@ def main():
         dy1, dw1, dv1 = e1.solve(ry, rw, rv)
         H1 = np.tril(e1.get_H())
         # sharded
-        es = cb.Engine(Q, np.ascontiguousarray(A[lo:hi]), G if p else None, lcd)
+        es = cb.Engine(Q, np.ascontiguousarray(A[lo:hi]), G if p else None, lcd, dist_chol=dist_chol)
         init_engine_comm(es)
         lam = es.factor_from_point(v[lo:hi], s[lo:hi])
         dy, dw, dv = es.solve(ry, rw, rv[lo:hi])
@@ -55,7 +60,7 @@ def main():
         errs.append(rel(es.mul_A(rv[lo:hi], trans=True), A.T @ rv))
         worst = max(worst, max(errs))
         if rank == 0:
-            print(prob["name"], "shard rows", hi - lo, "errs", ["%.1e" % e for e in errs], flush=True)
+            print(prob["name"], "n", n, "dist_chol", dist_chol, "shard rows", hi - lo, "errs", ["%.1e" % e for e in errs], flush=True)
         # full sharded solve vs single GPU
         sol1 = cb.conicIP(Q, prob["c"], A, prob["b"], cd, G if p else None, prob["d"] if p else None, optTol=1e-8)
         kk = lambda Q_, A_, G_, cd_: _gen(es)

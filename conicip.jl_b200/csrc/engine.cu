@@ -168,10 +168,12 @@ int form_H(cip_engine* h) {
   if (h->m_pad > 0) CIP_TRY(cone_scale_panel(h->cd, h->Fi, h->At4, h->Atil4, h->n_pad, h->m_pad, h->n, s));
   CIP_CUDA(cudaEventRecord(h->ev[1], s));
   const double* cin = (h->rank == 0) ? h->Qq4 : nullptr;
-  if (h->m_pad > 0) {
+  // rows of Atil beyond m_pad hold sqrt(rho)*G (constant): H' = Q + Atil'Atil + rho G'G, added on rank 0 only
+  const int k_rows = h->m_pad + ((h->rank == 0) ? h->aug_rows : 0);
+  if (k_rows > 0) {
     GemmArgs a{};
     a.lower = 1; a.ntm = a.ntn = h->n_pad / TILE; a.sym = 1;
-    a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = h->m_pad / 32;
+    a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = k_rows / 32;
     a.Cin = cin; a.Cout = h->H4; a.ldc = h->n_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
     CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, s));
   } else {
@@ -305,6 +307,7 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
   cip_engine* h = new cip_engine();
   *out = nullptr;
   h->opt.dist_chol = -1;
+  h->opt.aug_rho = -1.0;
   if (opts) memcpy(&h->opt, opts, std::min<size_t>(sizeof(cip_options), (size_t)opts->struct_size));
   else h->opt.device = -1;
   if (h->opt.device < 0) CIP_CUDA(cudaGetDevice(&h->device));
@@ -407,7 +410,14 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
   const size_t nn = (size_t)h->n_pad * h->n_pad;
   const size_t mn = (size_t)h->m_pad * h->n_pad;
   CIP_TRY(dev_alloc(h, &h->At4, mn));
-  CIP_TRY(dev_alloc(h, &h->Atil4, mn));
+  // augmentation rows (H + rho G'G keeps the Cholesky valid when H is singular on range(G'), as kktsolver_qr allows)
+  {
+    double rho = h->opt.aug_rho;
+    if (rho < 0) rho = (p > 0) ? 1.0 : 0.0;
+    h->aug_rho = (p > 0) ? rho : 0.0;
+    h->aug_rows = (h->aug_rho > 0) ? round_up(p, 32) : 0;
+  }
+  CIP_TRY(dev_alloc(h, &h->Atil4, (size_t)(h->m_pad + h->aug_rows) * h->n_pad));
   CIP_TRY(dev_alloc(h, &h->Qq4, nn));
   CIP_TRY(dev_alloc(h, &h->H4, nn));
   CIP_TRY(dev_alloc(h, &h->Winv, (size_t)h->n_pad * TILE));
@@ -468,8 +478,9 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
       }
       cudaFree(stg);
     }
-    CIP_TRY(make_q4_tensor_map(&h->mapAtil.map, h->Atil4, h->n_pad, h->m_pad / 4));
   }
+  if (h->m_pad + h->aug_rows > 0)
+    CIP_TRY(make_q4_tensor_map(&h->mapAtil.map, h->Atil4, h->n_pad, (h->m_pad + h->aug_rows) / 4));
   CIP_TRY(chol_make_plan(&h->cholH, h->H4, h->n_pad, h->Winv, h->info));
 
   // G
@@ -497,6 +508,8 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
       CIP_CUDA(cudaStreamSynchronize(s));
       if (stg) cudaFree(stg);
     }
+    if (h->aug_rows > 0)
+      CIP_TRY(transpose_scale_q4(h->Atil4, h->n_pad, h->m_pad, h->G4, h->p_pad, p, n, sqrt(h->aug_rho), s));
     CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, p, h->p_pad, 1.0, 1, s));
     if (h->opt.reg_eps_G != 0.0) CIP_TRY(add_diag_q4(h->Sbase4, h->p_pad, 0, p, h->opt.reg_eps_G, 1, s));
     CIP_TRY(make_q4_tensor_map(&h->mapZ.map, h->Z4, h->p_pad, h->n_pad / 4));
@@ -535,6 +548,7 @@ int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, c
   }
   cip_options o{};
   o.dist_chol = -1;
+  o.aug_rho = -1.0;
   if (opts) memcpy(&o, opts, std::min<size_t>(sizeof(o), (size_t)opts->struct_size));
   else o.device = -1;
   o.struct_size = sizeof(o);
@@ -719,6 +733,10 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   }
   CIP_TRY(allreduce(h, h->nv[1], h->n));
   CIP_TRY(vec_axpby(h->nv[2], 1.0, h->nv[0], 1.0, h->nv[1], h->n, s));
+  if (h->aug_rows > 0) {        // rhs += rho G' rw  (same (dy, dw) as the unaugmented system)
+    CIP_TRY(q4_mv_k(h->nv[4], h->G4, h->p_pad, h->p, h->n, h->pv[0], s));
+    CIP_TRY(vec_axpby(h->nv[2], 1.0, h->nv[2], h->aug_rho, h->nv[4], h->n, s));
+  }
   // 2x2 solve with H = L L' and the Schur complement on G (:299)
   CIP_TRY(chol_fwd(h->cholH, h->nv[2], h->nv[3], s));
   if (h->p) {

@@ -30,6 +30,8 @@ struct cip_engine {
   cip::ConeDesc cd{};
   cip::Scaling F{}, Fi{};
   bool have_scaling = false, have_factor = false;
+  int aug_rows = 0;        // rows of Atil4 beyond m_pad holding sqrt(aug_rho) * G
+  double aug_rho = 0.0;
   // work vectors
   double* nv[NV] = {};
   double* mv[MV] = {};

@@ -84,6 +84,13 @@ __global__ void scatter_csc_kernel(double* __restrict__ dst, int ld, const long 
   }
 }
 
+__global__ void transpose_scale_kernel(double* __restrict__ dst, int ldd, int k0, const double* __restrict__ src,
+                                       int lds, int R, int K, double scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // column of src (row of dst)
+  const int i = blockIdx.y;                              // row of src
+  if (j < K && i < R) dst[q4_index(j, k0 + i, ldd)] = scale * src[q4_index(i, j, lds)];
+}
+
 // out-partials[split][r] = sum over this split's k-quads of X[r, k] v[k]
 __global__ void __launch_bounds__(128)
 mv_rows_kernel(double* __restrict__ partial, const double* __restrict__ X, int ld, int R, int Kq,
@@ -213,6 +220,15 @@ int scatter_csc_q4(double* dst, int ld, int ncols, const long long* colptr, cons
                    const double* nzval, int base, int transpose, cudaStream_t s) {
   if (ncols <= 0) return 0;
   scatter_csc_kernel<<<ncols, 128, 0, s>>>(dst, ld, colptr, rowval, nzval, base, transpose);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+int transpose_scale_q4(double* dst, int ldd, int k0, const double* src, int lds, int R, int K, double scale,
+                       cudaStream_t s) {
+  if (R <= 0 || K <= 0) return 0;
+  dim3 grid((K + 127) / 128, R);
+  transpose_scale_kernel<<<grid, 128, 0, s>>>(dst, ldd, k0, src, lds, R, K, scale);
   CIP_CHECK_LAUNCH();
   return 0;
 }

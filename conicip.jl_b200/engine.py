@@ -36,7 +36,7 @@ class Engine:
     """LEVEL-1 object: `kktsolver(Q, A, G, cone_dims)` (src/ConicIP.jl:667)."""
 
     def __init__(self, Q, A, G, cone_dims, *, reg_delta=0.0, reg_eps_G=0.0, device=-1,
-                 use_torch_stream=True, dist_chol=-1):
+                 use_torch_stream=True, dist_chol=-1, aug_rho=-1.0):
         L = lib()
         self.cone_dims = [(t, int(k)) for t, k in cone_dims]
         self.cone_type = np.array([CONE_CODE[t] for t, _ in self.cone_dims], dtype=np.int32)
@@ -51,6 +51,7 @@ class Engine:
         opts.reg_eps_G = reg_eps_G
         opts.q_kind = 0
         opts.dist_chol = dist_chol
+        opts.aug_rho = aug_rho
         self._torch = None
         self._use_torch_stream = use_torch_stream
         self.last_factor_status = 0

@@ -29,6 +29,7 @@ struct Options            # mirrors cip_options
     q_kind::Cint
     verbose::Cint
     dist_chol::Cint
+    aug_rho::Cdouble
 end
 
 lasterr() = unsafe_string(ccall((:cip_last_error, LIB), Cstring, ()))
@@ -56,7 +57,7 @@ mutable struct Engine
             Qs = SparseMatrixCSC{Float64,Int64}(sparse(Q)); As = SparseMatrixCSC{Float64,Int64}(A)
             Gs = SparseMatrixCSC{Float64,Int64}(sparse(G))
             ct = Cint[CONE_CODE[t] for (t, _) in cone_dims]; cdim = Cint[k for (_, k) in cone_dims]
-            opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, Cint(2), Cint(0), Cint(-1)))
+            opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, Cint(2), Cint(0), Cint(-1), -1.0))
             hp = Ref{Ptr{Cvoid}}(C_NULL)
             GC.@preserve Qs As Gs begin
                 rc = ccall((:cip_create_csc, LIB), Cint,
@@ -75,7 +76,7 @@ mutable struct Engine
         Gd = Matrix{Float64}(G)
         ct = Cint[CONE_CODE[t] for (t, _) in cone_dims]
         cdim = Cint[k for (_, k) in cone_dims]
-        opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, qk, Cint(0), Cint(-1)))
+        opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, qk, Cint(0), Cint(-1), -1.0))
         hp = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:cip_create, LIB), Cint,
                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint,

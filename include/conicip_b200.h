@@ -57,6 +57,9 @@ typedef struct cip_options {
   int    q_kind;        /* 0 dense n*n (ldq), 1 diagonal (Q points to n doubles), 2 zero  */
   int    verbose;
   int    dist_chol;     /* sharded handles: 0 replicated Cholesky, 1 block-cyclic distributed, -1 auto */
+  double aug_rho;       /* equality block: factor H + rho*G'G (and add rho*G'rw to the rhs) so that H may be
+                           singular on range(G') as kktsolver_qr allows (src/kktsolvers.jl:35); same solution.
+                           < 0: auto (1.0 when p > 0), 0: off */
 } cip_options;
 
 typedef struct cip_stats_t {

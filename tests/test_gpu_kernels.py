@@ -160,6 +160,8 @@ def test_form_H_cholesky_and_solve(case):
     Fi = Fo.inv_adjoint()
     At = Fi.mul(A)
     Href = Q + At.T @ At                                       # src/kktsolvers.jl:33-34
+    if p:
+        Href = Href + G.T @ G                                  # default augmentation rho = 1 (opts.aug_rho)
     eng.form_H()
     assert rel(np.tril(eng.get_H()), np.tril(Href)) < KTOL
     assert eng.factor_H() == 0
@@ -266,6 +268,29 @@ def test_error_behaviour():
     eng = cb.Engine(-np.eye(3), np.zeros((2, 3)), None, [("R", 2)])
     st = eng.factor(cb.Block([cb.Diagonal(np.ones(2))]))
     assert st == 1 and "pivot" in cb._lib.last_error()
+    eng.close()
+
+
+def test_singular_H_with_equalities_like_kktsolver_qr():
+    """H singular on range(G') (LP with a free variable): kktsolver_qr handles it (src/kktsolvers.jl:35),
+    a plain Cholesky of H cannot.  The default augmentation H + rho G'G gives the same solution."""
+    import conicip_b200 as cb
+    # variables (x1, x2, t): minimise t  s.t.  t - x1 - x2 = 0,  x1 >= 1, x2 >= 2   (t is free: H_tt = 0)
+    Q = np.zeros((3, 3))
+    c = np.array([0.0, 0.0, -1.0])                       # minimise -c'y = t
+    A = np.array([[1.0, 0, 0], [0, 1.0, 0]])
+    b = np.array([1.0, 2.0])
+    G = np.array([[-1.0, -1.0, 1.0]])
+    d = np.array([0.0])
+    so = O.conicIP(Q, c, A, b, [("R", 2)], G, d, optTol=1e-8, kktsolver=O.kktsolver_qr)
+    s = cb.conicIP(Q, c, A, b, [("R", 2)], G, d, optTol=1e-8)
+    assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1
+    assert np.allclose(s.y, [1.0, 2.0, 3.0], atol=1e-6) and rel(s.y, so.y) < 1e-6 and rel(s.v, so.v) < 1e-6
+    sn = cb.conicIP_native(Q, c, A, b, [("R", 2)], G, d, optTol=1e-8)
+    assert sn.status == "Optimal" and rel(sn.y, so.y) < 1e-6
+    # without the augmentation the factorisation reports the failing pivot (status > 0)
+    eng = cb.Engine(Q, A, G, [("R", 2)], aug_rho=0.0)
+    assert eng.factor(cb.Block([cb.Diagonal(np.ones(2))])) == 3
     eng.close()
 
 

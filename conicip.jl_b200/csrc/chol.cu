@@ -34,6 +34,8 @@ __device__ __forceinline__ double fast_rcp(double d) {
 //     triangle of S.
 constexpr int SB = 32;           // sub-panel width
 constexpr int PLD = 132;         // leading dimension of the transposed sub-panel copy P[k][i]
+constexpr int SWEEP_WARPS = 8;   // warps that run the column sweep of a sub-panel
+constexpr int SWEEP_ROWS = NB / SWEEP_WARPS;   // matrix elements per thread during the sweep
 
 __global__ void __launch_bounds__(512, 1)
 potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W, int* info) {
@@ -54,44 +56,45 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   __syncthreads();
 
   for (int c0 = 0; c0 < NB; c0 += SB) {
-    // ---- sub-panel: column j = c0 + lane, rows i_e = w + 16 e
-    const int j = c0 + lane;
-    double a[8];
+    // ---- sub-panel sweep on warps 0..7 only (column j = c0 + lane, rows i_e = w + 8 e, 16 elements per
+    //      thread): every warp repeats the pivot reciprocal and pays for the barrier, so fewer, fatter
+    //      warps shorten the per-column chain; warps 8..15 wait at the block barrier below.
+    if (w < SWEEP_WARPS) {
+      const int j = c0 + lane;
+      double a[SWEEP_ROWS];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = w + 16 * e;
-      a[e] = (i >= j) ? S[i * SLD + j] : 0.0;
-    }
-    double dj = 1.0;
-    for (int k = 0; k < SB; ++k) {
-      double* ck = colk + (k & 1) * NB;
-      if (lane == k) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ck[w + 16 * e] = a[e];
+      for (int e = 0; e < SWEEP_ROWS; ++e) {
+        const int i = w + SWEEP_WARPS * e;
+        a[e] = (i >= j) ? S[i * SLD + j] : 0.0;
       }
-      __syncthreads();
-      double d = ck[c0 + k];
-      if (!(d > 0.0)) {
-        if (tid == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
-        d = 1.0;
-      }
-      if (lane == k) dj = d;
-      if (lane > k) {
-        const double t = ck[j] * fast_rcp(d);
+      double dj = 1.0;
+      for (int k = 0; k < SB; ++k) {
+        double* ck = colk + (k & 1) * NB;
+        if (lane == k) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int i = w + 16 * e;
-          if (i >= j) a[e] = fma(-ck[i], t, a[e]);
+          for (int e = 0; e < SWEEP_ROWS; ++e) ck[w + SWEEP_WARPS * e] = a[e];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_WARPS * 32) : "memory");
+        double d = ck[c0 + k];
+        const bool bad = !(d > 0.0);
+        if (bad && tid == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
+        d = bad ? 1.0 : d;
+        if (lane == k) dj = d;
+        if (lane > k) {
+          const double t = ck[j] * fast_rcp(d);
+#pragma unroll
+          for (int e = 0; e < SWEEP_ROWS; ++e) {
+            const int i = w + SWEEP_WARPS * e;
+            if (i >= j) a[e] = fma(-ck[i], t, a[e]);
+          }
         }
       }
-    }
-    // scale: L[i][j] = a / sqrt(d_j); publish to S and to the transposed copy P[lane][i]
-    {
+      // scale: L[i][j] = a / sqrt(d_j); publish to S and to the transposed copy P[lane][i]
       const double rs = 1.0 / sqrt(dj);
-      if (w == (j & 15)) dinv[j] = rs;             // exactly one thread per column (the owner of (j,j))
+      if (w == (j & (SWEEP_WARPS - 1))) dinv[j] = rs;     // exactly one thread per column (the owner of (j,j))
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = w + 16 * e;
+      for (int e = 0; e < SWEEP_ROWS; ++e) {
+        const int i = w + SWEEP_WARPS * e;
         double v = 0.0;
         if (i > j) v = a[e] * rs;
         else if (i == j) v = dj * rs;
@@ -157,19 +160,30 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   // ---- inverse.  X(r,c), r > c, lives at S[c][r]; X(r,r) = dinv[r].
 #define XG(r, c) S[(c) * SLD + (r)]
   {
-    // diagonal 32x32 blocks: 4 blocks x 32 columns x 4 lanes = 512 threads, no block barrier
+    // diagonal 32x32 blocks: 4 blocks x 32 columns x 4 lanes = 512 threads, no block barrier.  All
+    // groups of a warp walk the same row index i (columns that start later are predicated off), so
+    // the warp stays convergent instead of serialising eight 4-lane paths.
     const int blk = tid >> 7, jl = (tid & 127) >> 2, part = tid & 3;
-    const unsigned gmask = 0xFu << (lane & ~3);
     const int b0 = blk * SB, jc = b0 + jl;
     const double xjj = dinv[jc];
-    for (int i = jc + 1; i < b0 + SB; ++i) {
+    for (int i = b0 + 1; i < b0 + SB; ++i) {
+      const bool active = i > jc;
       const double* Li = S + i * SLD;
-      double sum = (part == 0) ? Li[jc] * xjj : 0.0;
-      for (int k = jc + 1 + part; k < i; k += 4) sum = fma(Li[k], XG(k, jc), sum);
-      sum += __shfl_xor_sync(gmask, sum, 1);
-      sum += __shfl_xor_sync(gmask, sum, 2);
-      if (part == 0) XG(i, jc) = -sum * dinv[i];
-      __syncwarp(gmask);
+      double s0 = 0.0, s1 = 0.0;
+      if (active) {
+        if (part == 0) s0 = Li[jc] * xjj;
+        int k = jc + 1 + part;
+        for (; k + 4 < i; k += 8) {
+          s0 = fma(Li[k], XG(k, jc), s0);
+          s1 = fma(Li[k + 4], XG(k + 4, jc), s1);
+        }
+        if (k < i) s0 = fma(Li[k], XG(k, jc), s0);
+      }
+      double sum = s0 + s1;
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (active && part == 0) XG(i, jc) = -sum * dinv[i];
+      __syncwarp();
     }
   }
   __syncthreads();

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <limits>
 #include <vector>
 
@@ -85,11 +86,10 @@ struct Ipm {
     ck(cip_maxstep(h, x1, d1, scale, &a1));
     ck(cip_maxstep(h, x2, d2, scale, &a2));
     if (h->comm) {
-      // min via sum of indicator is not available; exchange through the engine's all-reduce on -log? no:
-      // use the identity min(a) = -max(-a) with an all-gather emulated by a sum of one-hot slots.
+      // global min through the engine's sum all-reduce: every rank writes its two values into its own
+      // slots of a zero vector (an all-gather), +Inf included (Inf + 0 = Inf stays in its slot)
       std::vector<double> slot(2 * h->nranks, 0.0);
       slot[2 * h->rank] = a1; slot[2 * h->rank + 1] = a2;
-      // +Inf cannot travel through a sum with zeros from other ranks (0 + Inf = Inf is fine, Inf only in own slot)
       double* dslot = vec(2 * h->nranks);
       cudaMemcpyAsync(dslot, slot.data(), sizeof(double) * slot.size(), cudaMemcpyHostToDevice, st);
       ck(engine_allreduce(h, dslot, slot.size()));
@@ -162,11 +162,6 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
   double *Qy = I.vec(n), *Gtw = I.vec(n), *Atv = I.vec(n), *tn1 = I.vec(n), *Ay = I.vec(m), *tp1 = I.vec(p);
   if (I.rc) return I.rc;
 
-  {
-    auto nb = I.dots({{c, c, n}, {d, d, p}}, {{b, b, m}});
-    res->seconds = 0;
-    (void)nb;
-  }
   const auto n0 = I.dots({{c, c, n}, {d, d, p}}, {{b, b, m}});
   const double normc = std::sqrt(n0[0]);
   const double normd = p ? std::sqrt(n0[1]) : -INFINITY;
@@ -204,7 +199,6 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
 
   double optBest = INFINITY;
   int status = CIP_STATUS_NONE;
-  bool nan_y = false, nan_vw = false;
   double yscale = 1.0, vwscale = 1.0;
 
   for (int Iter = 1; Iter <= o.maxIters && I.rc == 0; ++Iter) {
@@ -257,7 +251,7 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
         const double p_ecos = pu / (std::fmax(1.0, normc) * std::fabs(dty_btv));
         p_infeas = (std::isnan(p_cvx) || std::isnan(p_ecos)) ? nanv() : std::fmax(p_cvx, p_ecos);
       }
-      if (p_infeas < o.infeasTol) { status = CIP_STATUS_INFEASIBLE; nan_y = true; vwscale = 1.0 / -dty_btv; }
+      if (p_infeas < o.infeasTol) { status = CIP_STATUS_INFEASIBLE; vwscale = 1.0 / -dty_btv; }
       const double d1 = m_glob == 0 ? -INFINITY : std::sqrt(ays2);
       const double d2 = p == 0 ? -INFINITY : std::sqrt(gy2);
       const double d3 = std::isfinite(yy) ? std::sqrt(qy2) : nanv();
@@ -267,7 +261,7 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
         const double a2 = std::fmax(d1, std::fmax(d2, d3)) / std::sqrt(yy);
         d_infeas = (std::isnan(a1) || std::isnan(a2) || std::isnan(d3)) ? nanv() : std::fabs(std::fmax(a1, a2));
       }
-      if (d_infeas < o.infeasTol) { status = CIP_STATUS_UNBOUNDED; nan_y = false; nan_vw = true; yscale = 1.0 / std::fabs(cty); }
+      if (d_infeas < o.infeasTol) { status = CIP_STATUS_UNBOUNDED; yscale = 1.0 / std::fabs(cty); }
     }
     if (o.verbose)
       printf(" %6d  | %8.1e %8.1e %8.1e | % 8.1e % 8.1e | mu %8.1e\n", Iter, rDu, rPr, rCp, res->pobj, res->dobj, mu);
@@ -346,7 +340,6 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
     I.fill(z.w, nanv(), p);
     I.fill(z.v, nanv(), m);
   }
-  (void)nan_y; (void)nan_vw;
   if (y_out) CIP_CUDA(cudaMemcpyAsync(y_out, z.y, sizeof(double) * n, cudaMemcpyDefault, I.st));
   if (w_out && p) CIP_CUDA(cudaMemcpyAsync(w_out, z.w, sizeof(double) * p, cudaMemcpyDefault, I.st));
   if (v_out && m) CIP_CUDA(cudaMemcpyAsync(v_out, z.v, sizeof(double) * m, cudaMemcpyDefault, I.st));

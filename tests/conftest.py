@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    # the shared library is git-ignored: build it on first use (nvcc cross-compiles without a GPU)
+    so = os.path.join(ROOT, "conicip.jl_b200", "libconicip_b200.so")
+    if not os.path.exists(so):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _has_gpu():

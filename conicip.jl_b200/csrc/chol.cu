@@ -3,6 +3,8 @@
 //                        L21  = A21 * inv(L11)'      -> gemm_nt (DMMA tiles)
 //                        A22 -= L21 * L21'           -> gemm_nt (lower, same tiles as the SYRK)
 // Replaces LAPACK qr/lu at src/kktsolvers.jl:35,:295 and the solves at :39-48,:299.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "nccl_dl.h"
 
@@ -490,7 +492,11 @@ int update_outer_panel(const CholPlan& p, int OUTER, int J, int Jc, cudaStream_t
 }  // namespace
 
 int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
-  constexpr int OUTER = 4;
+  // outer panel width in 128-column panels: with >= 4 ranks the factorisation is bound by the panel chain
+  // (factor -> broadcast -> next-panel update), which narrower outer panels shorten; the bulk updates are
+  // only 1/nranks of the work per GPU, so their lower K = 256 efficiency does not matter there.
+  int OUTER = (d.nranks >= 4) ? 2 : 4;
+  if (const char* env = getenv("CIP_DIST_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
   const NcclApi* api = nccl_api();
   if (!api) return -1;
   const int smem = (NB * SLD + 3 * NB + SB * PLD) * (int)sizeof(double);

@@ -194,7 +194,7 @@ int factor_H(cip_engine* h) {
   // opts.dist_chol: 0 = replicated, 1 = distributed, -1/unset = distributed iff >= 2 outer panels per rank
   bool dist = false;
   if (h->comm && h->nranks > 1) {
-    const int outer_panels = (h->cholH.npanels + 3) / 4;
+    const int outer_panels = (h->cholH.npanels + 3) / 4;   // 512-column units
     int mode = h->opt.dist_chol;
     if (const char* env = getenv("CIP_DIST_CHOL")) mode = atoi(env);
     dist = (mode == 1) || (mode != 0 && outer_panels >= 2 * h->nranks);

@@ -492,10 +492,8 @@ int update_outer_panel(const CholPlan& p, int OUTER, int J, int Jc, cudaStream_t
 }  // namespace
 
 int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
-  // outer panel width in 128-column panels: with >= 4 ranks the factorisation is bound by the panel chain
-  // (factor -> broadcast -> next-panel update), which narrower outer panels shorten; the bulk updates are
-  // only 1/nranks of the work per GPU, so their lower K = 256 efficiency does not matter there.
-  int OUTER = (d.nranks >= 4) ? 2 : 4;
+  // outer panel width in 128-column panels (measured at C4 on 4 GPUs: 4 -> 39.3 ms, 2 -> 41.1 ms)
+  int OUTER = 4;
   if (const char* env = getenv("CIP_DIST_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
   const NcclApi* api = nccl_api();
   if (!api) return -1;

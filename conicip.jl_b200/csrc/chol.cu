@@ -58,87 +58,51 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   __syncthreads();
 
   for (int c0 = 0; c0 < NB; c0 += SB) {
-    // ---- (A) 32x32 diagonal block on warp 0: lane i keeps row i in registers, columns travel by shuffle,
-    //      no barrier on the dependent chain (shuffle -> reciprocal -> FMA per column).  Pivot scaling is
-    //      deferred: a[j] holds L[i][j] * L[j][j] until the end.
-    if (w == 0) {
-      const int gi = c0 + lane;
-      double a[SB];
+    // ---- sub-panel sweep (column j = c0 + lane, rows i_e = w + SWEEP_WARPS e): the per-column chain is
+    //      update -> publish -> barrier -> pivot reciprocal, so elements per thread are kept small.
+    if (w < SWEEP_WARPS) {
+      const int j = c0 + lane;
+      double a[SWEEP_ROWS];
 #pragma unroll
-      for (int j = 0; j < SB; ++j) a[j] = (j <= lane) ? S[gi * SLD + c0 + j] : 0.0;
-#pragma unroll
-      for (int k = 0; k < SB; ++k) {
-        double dk = __shfl_sync(0xffffffffu, a[k], k);
-        const bool bad = !(dk > 0.0);
-        if (bad && lane == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
-        dk = bad ? 1.0 : dk;
-        if (bad && lane == k) a[k] = 1.0;
-        const double lik = a[k] * fast_rcp(dk);
-#pragma unroll
-        for (int j = k + 1; j < SB; ++j) {
-          const double ajk = __shfl_sync(0xffffffffu, a[k], j);
-          a[j] = fma(-lik, ajk, a[j]);
-        }
+      for (int e = 0; e < SWEEP_ROWS; ++e) {
+        const int i = w + SWEEP_WARPS * e;
+        a[e] = (i >= j) ? S[i * SLD + j] : 0.0;
       }
-      // lane j's a[j] is now the pivot d_j; scale columns and publish L (S, transposed copy P) and 1/L_jj
       double dj = 1.0;
+      for (int k = 0; k < SB; ++k) {
+        double* ck = colk + (k & 1) * NB;
+        if (lane == k) {
 #pragma unroll
-      for (int j = 0; j < SB; ++j) if (j == lane) dj = a[j];
-      const double rs = 1.0 / sqrt(dj);
-      dinv[gi] = rs;
+          for (int e = 0; e < SWEEP_ROWS; ++e) ck[w + SWEEP_WARPS * e] = a[e];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_WARPS * 32) : "memory");
+        double d = ck[c0 + k];
+        const bool bad = !(d > 0.0);
+        if (bad && tid == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
+        d = bad ? 1.0 : d;
+        if (lane == k) dj = d;
+        if (lane > k) {
+          const double t = ck[j] * fast_rcp(d);
 #pragma unroll
-      for (int j = 0; j < SB; ++j) {
-        const double rsj = __shfl_sync(0xffffffffu, rs, j);
-        const double v = (j < lane) ? a[j] * rsj : ((j == lane) ? dj * rs : 0.0);
-        S[gi * SLD + c0 + j] = v;
-        P[j * PLD + gi] = v;
-      }
-      __syncwarp();
-      // inverse of the block, lane j owns column j: x[i] = -(sum_{k=j}^{i-1} L[i][k] x[k]) / L[i][i]
-      double x[SB];
-#pragma unroll
-      for (int i = 0; i < SB; ++i) x[i] = 0.0;
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        if (i == lane) x[i] = rs;
-        if (i > 0) {
-          double s0 = 0.0, s1 = 0.0;
-          const double* Li = S + (c0 + i) * SLD + c0;
-#pragma unroll
-          for (int k = 0; k < i; ++k) {          // x[k] is zero for k < lane, so no predicate is needed
-            if (k & 1) s1 = fma(Li[k], x[k], s1);
-            else s0 = fma(Li[k], x[k], s0);
+          for (int e = 0; e < SWEEP_ROWS; ++e) {
+            const int i = w + SWEEP_WARPS * e;
+            if (i >= j) a[e] = fma(-ck[i], t, a[e]);
           }
-          if (i > lane) x[i] = -(s0 + s1) * dinv[c0 + i];
         }
       }
-      __syncwarp();
-      // X(r,c), r > c, lives transposed in the upper triangle: S[c][r]
+      // scale: L[i][j] = a / sqrt(d_j); publish to S and to the transposed copy P[lane][i]
+      const double rs = 1.0 / sqrt(dj);
+      if (w == (j & (SWEEP_WARPS - 1))) dinv[j] = rs;     // exactly one thread per column (the owner of (j,j))
 #pragma unroll
-      for (int i = 0; i < SB; ++i)
-        if (i > lane) S[gi * SLD + c0 + i] = x[i];
-    }
-    __syncthreads();
-    // ---- (B) rows below the block: Y = A_sub * inv(L_pp)' for all rows r >= c0 + 32 (the in-block TRSM)
-    {
-      const int jc = lane;                        // column of the sub-panel
-      double y[NB / 16];
-      int nrow = 0;
-      for (int r = c0 + SB + w; r < NB; r += 16, ++nrow) {
-        const double* Ar = S + r * SLD + c0;
-        double s0 = Ar[jc] * dinv[c0 + jc], s1 = 0.0;        // k == jc term: X[jc][jc] = 1 / L_jj
-        for (int k = 0; k < jc; ++k) {                       // X[jc][k], k < jc, sits at S[c0+k][c0+jc]
-          const double xk = S[(c0 + k) * SLD + c0 + jc];
-          if (k & 1) s1 = fma(Ar[k], xk, s1);
-          else s0 = fma(Ar[k], xk, s0);
+      for (int e = 0; e < SWEEP_ROWS; ++e) {
+        const int i = w + SWEEP_WARPS * e;
+        double v = 0.0;
+        if (i > j) v = a[e] * rs;
+        else if (i == j) v = dj * rs;
+        if (i >= c0) {
+          S[i * SLD + j] = v;
+          P[lane * PLD + i] = v;
         }
-        y[nrow] = s0 + s1;
-      }
-      __syncthreads();                            // every thread has read its A rows before anyone overwrites them
-      nrow = 0;
-      for (int r = c0 + SB + w; r < NB; r += 16, ++nrow) {
-        S[r * SLD + c0 + jc] = y[nrow];
-        P[jc * PLD + r] = y[nrow];
       }
     }
     __syncthreads();
@@ -196,6 +160,34 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
 
   // ---- inverse.  X(r,c), r > c, lives at S[c][r]; X(r,r) = dinv[r].
 #define XG(r, c) S[(c) * SLD + (r)]
+  {
+    // diagonal 32x32 blocks: 4 blocks x 32 columns x 4 lanes = 512 threads, no block barrier.  All
+    // groups of a warp walk the same row index i (columns that start later are predicated off), so
+    // the warp stays convergent instead of serialising eight 4-lane paths.
+    const int blk = tid >> 7, jl = (tid & 127) >> 2, part = tid & 3;
+    const int b0 = blk * SB, jc = b0 + jl;
+    const double xjj = dinv[jc];
+    for (int i = b0 + 1; i < b0 + SB; ++i) {
+      const bool active = i > jc;
+      const double* Li = S + i * SLD;
+      double s0 = 0.0, s1 = 0.0;
+      if (active) {
+        if (part == 0) s0 = Li[jc] * xjj;
+        int k = jc + 1 + part;
+        for (; k + 4 < i; k += 8) {
+          s0 = fma(Li[k], XG(k, jc), s0);
+          s1 = fma(Li[k + 4], XG(k + 4, jc), s1);
+        }
+        if (k < i) s0 = fma(Li[k], XG(k, jc), s0);
+      }
+      double sum = s0 + s1;
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (active && part == 0) XG(i, jc) = -sum * dinv[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
   for (int dlt = 1; dlt < NB / SB; ++dlt) {
     const int nblk = NB / SB - dlt;
     // T_b = sum_{kk} L(ib, kk) * X(kk, jb)   for block pairs (ib, jb) = (b + dlt, b)

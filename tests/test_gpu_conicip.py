@@ -130,3 +130,50 @@ def test_kktsolver_three_level_protocol():
     assert np.linalg.norm(Q @ a + G.T @ b - A.T @ c - x) < 1e-10 * np.linalg.norm(x) * 10
     assert np.linalg.norm(G @ a - y) < 1e-10
     assert np.linalg.norm(A @ a + 4.0 * c - z) < 1e-10 * np.linalg.norm(z) * 10
+
+
+def _dense_h_problem(seed=0, n=10):
+    rng = np.random.default_rng(seed)
+    h = rng.standard_normal(n)
+    H = np.outer(h, h)                                   # rank-1 "H = randn(n); H = H*H'" (runtests.jl:275-277)
+    c = np.arange(1.0, n + 1)
+    return H, H @ c, n, rng
+
+
+def test_simplex_dense_rank1_H():
+    """runtests.jl:271-303 (NumPy data): projection onto the simplex with a rank-one H.  H + A'W^-2A is
+    positive definite because A = I."""
+    import conicip_b200 as cb
+    H, c, n, _ = _dense_h_problem()
+    G, d = np.ones((1, n)), np.array([1.0])
+    s = cb.conicIP(H, c, np.eye(n), np.zeros(n), [("R", n)], G, d, optTol=1e-7)
+    so = O.conicIP(H, c, np.eye(n), np.zeros(n), [("R", n)], G, d, optTol=1e-7, kktsolver=O.kktsolver_qr)
+    assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1
+    assert rel(s.y, so.y) < 1e-5 and abs(s.y.sum() - 1.0) < 1e-7 and s.y.min() > -1e-9
+
+
+def test_linear_constraints_comparison():
+    """runtests.jl:328-356: equalities through G must give the same y as the same equalities written as
+    two inequality blocks [A; G; -G] >= [b; d; -d]."""
+    import conicip_b200 as cb
+    H, c, n, rng = _dense_h_problem(seed=1)
+    H = H + 0.1 * np.eye(n)
+    A, b = np.eye(n), np.zeros(n)
+    G, d = rng.random((6, n)), np.zeros(6)
+    y1 = cb.conicIP(H, c, A, b, [("R", n)], G, d, optTol=1e-7).y
+    A2, b2 = np.vstack([A, G, -G]), np.concatenate([b, d, -d])
+    y2 = cb.conicIP(H, c, A2, b2, [("R", n + 12)], optTol=1e-7).y
+    assert np.linalg.norm(y1 - y2) < 1e-3                                 # the reference's tolerance
+
+
+def test_infeasible_with_linear_constraints():
+    """runtests.jl:462-485: x >= 0 together with x1 = -1."""
+    import conicip_b200 as cb
+    H, c, n, _ = _dense_h_problem(seed=2)
+    G = np.zeros((1, n)); G[0, 0] = 1.0
+    s = cb.conicIP(H, c, np.eye(n), np.zeros(n), [("R", n)], G, np.array([-1.0]), optTol=1e-7)
+    so = O.conicIP(H, c, np.eye(n), np.zeros(n), [("R", n)], G, np.array([-1.0]), optTol=1e-7,
+                   kktsolver=O.kktsolver_qr)
+    assert s.status == so.status == "Infeasible"
+    sn = cb.conicIP_native(H, c, np.eye(n), np.zeros(n), [("R", n)], G, np.array([-1.0]), optTol=1e-7)
+    assert sn.status == "Infeasible" and np.all(np.isnan(sn.y))

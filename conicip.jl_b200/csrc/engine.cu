@@ -297,15 +297,32 @@ int upload_csc(cip_engine* h, double* dst, int ld, const cip_csc* M, int transpo
   return rc;
 }
 
+int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs, int ncones,
+                const int* cone_type, const int* cone_dim, const cip_options* opts);
+
+// allocates the handle, builds it, and releases everything again if any step fails
 int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
                 const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs, int ncones,
                 const int* cone_type, const int* cone_dim, const cip_options* opts) {
-  if (!out || n <= 0 || m < 0 || p < 0 || ncones < 0) {
+  if (out) *out = nullptr;
+  if (!out || n <= 0 || m < 0 || p < 0 || ncones < 0 || (ncones > 0 && (!cone_type || !cone_dim))) {
     set_error("cip_create: bad dimensions n=%d m=%d p=%d ncones=%d", n, m, p, ncones);
     return -1;
   }
   cip_engine* h = new cip_engine();
-  *out = nullptr;
+  const int rc = create_body(h, n, m, p, Q, ldq, A, lda, G, ldg, Qs, As, Gs, ncones, cone_type, cone_dim, opts);
+  if (rc != 0) {
+    cip_destroy(h);            // every member is null-checked there
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs, int ncones,
+                const int* cone_type, const int* cone_dim, const cip_options* opts) {
   h->opt.dist_chol = -1;
   h->opt.aug_rho = -1.0;
   if (opts) memcpy(&h->opt, opts, std::min<size_t>(sizeof(cip_options), (size_t)opts->struct_size));
@@ -319,7 +336,6 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
     if (prop.major != 10) {
       set_error("conicip_b200 requires an sm_100a device (found sm_%d%d); there is no fallback path", prop.major,
                 prop.minor);
-      delete h;
       return -3;
     }
   }
@@ -525,7 +541,6 @@ int create_impl(cip_handle* out, int n, int m, int p, const double* Q, int ldq, 
   CIP_TRY(dev_alloc(h, &h->scalar, 8));
   CIP_CUDA(cudaStreamSynchronize(s));
   h->st.n = n; h->st.m = m; h->st.p = p; h->st.n_pad = h->n_pad; h->st.m_pad = h->m_pad; h->st.p_pad = h->p_pad;
-  *out = h;
   return 0;
 }
 
@@ -561,7 +576,7 @@ int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, c
 int cip_destroy(cip_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->own_stream) cudaStreamSynchronize(h->stream);
   if (h->comm) {
     const NcclApi* api = nccl_api();
     if (api) api->CommDestroy(h->comm);
@@ -576,7 +591,8 @@ int cip_destroy(cip_handle h) {
   chol_free_plan(&h->cholH);
   chol_free_plan(&h->cholS);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(h->own_stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  cudaGetLastError();
   delete h;
   return 0;
 }

@@ -102,6 +102,15 @@ def run_reference(args, n, m):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all the host threads it can
+    ncpu = str(os.cpu_count() or 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = ncpu
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=int(ncpu))
+    except Exception:
+        pass
     times = []
     desc, threads = "", 1
     for i in range(args.warmup + args.steps):

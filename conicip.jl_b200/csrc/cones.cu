@@ -61,6 +61,26 @@ __global__ void nt_r_kernel(ConeDesc c, const double* __restrict__ v, const doub
   }
 }
 
+// all rows in R cones (LP / QP): no per-row cone lookup, two rows per iteration with 16-byte accesses
+__global__ void nt_r_all_kernel(int m, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
+                                Scaling Fi, double* __restrict__ lambda) {
+  const int m2 = m >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
+    const double2 vv = reinterpret_cast<const double2*>(v)[i], ss = reinterpret_cast<const double2*>(s)[i];
+    const double2 f = make_double2(sqrt(ss.x / vv.x), sqrt(ss.y / vv.y));
+    reinterpret_cast<double2*>(F.a)[i] = f;
+    reinterpret_cast<double2*>(F.b)[i] = make_double2(0.0, 0.0);
+    reinterpret_cast<double2*>(Fi.a)[i] = make_double2(1.0 / f.x, 1.0 / f.y);
+    reinterpret_cast<double2*>(Fi.b)[i] = make_double2(0.0, 0.0);
+    reinterpret_cast<double2*>(lambda)[i] = make_double2(f.x * vv.x, f.y * vv.y);
+  }
+  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int i = m - 1;
+    const double f = sqrt(s[i] / v[i]);
+    F.a[i] = f; F.b[i] = 0.0; Fi.a[i] = 1.0 / f; Fi.b[i] = 0.0; lambda[i] = f * v[i];
+  }
+}
+
 __global__ void nt_kind_kernel(ConeDesc c, Scaling F, Scaling Fi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.ncones) return;
@@ -171,6 +191,16 @@ __global__ void prod_r_kernel(ConeDesc c, const double* __restrict__ x, const do
     o[i] = divide ? x[i] / y[i] : x[i] * y[i];   // drp! / xrp!, src/ConicIP.jl:305-315
   }
 }
+__global__ void prod_r_all_kernel(int m, const double* __restrict__ x, const double* __restrict__ y,
+                                  double* __restrict__ o, int divide) {
+  const int m2 = m >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
+    const double2 a = reinterpret_cast<const double2*>(x)[i], b = reinterpret_cast<const double2*>(y)[i];
+    reinterpret_cast<double2*>(o)[i] = divide ? make_double2(a.x / b.x, a.y / b.y) : make_double2(a.x * b.x, a.y * b.y);
+  }
+  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) o[m - 1] = divide ? x[m - 1] / y[m - 1] : x[m - 1] * y[m - 1];
+}
+
 template <int G>
 __global__ void prod_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
                               double* __restrict__ o) {
@@ -225,6 +255,33 @@ __global__ void maxstep_r_kernel(ConeDesc c, const double* __restrict__ x, const
   mn = warp_min(mn);
   if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
 }
+__device__ __forceinline__ double rp_candidate(double x, const double* d, size_t i, double d_scale) {
+  if (d) {
+    const double di = d[i] / d_scale;
+    return di > 0 ? x / di : CUDART_INF;                           // maxstep_rp, :212-225
+  }
+  return x > 0 ? 0.0 : -1.0 + x;                                   // :227-240
+}
+__global__ void maxstep_r_all_kernel(int m, const double* __restrict__ x, const double* __restrict__ d,
+                                     double d_scale, unsigned long long* key) {
+  double mn = CUDART_INF;
+  const int m2 = m >> 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
+    const double2 xx = reinterpret_cast<const double2*>(x)[i];
+    if (d) {
+      const double2 dd = reinterpret_cast<const double2*>(d)[i];
+      const double d0 = dd.x / d_scale, d1 = dd.y / d_scale;
+      if (d0 > 0) mn = fmin(mn, xx.x / d0);
+      if (d1 > 0) mn = fmin(mn, xx.y / d1);
+    } else {
+      mn = fmin(mn, fmin(xx.x > 0 ? 0.0 : -1.0 + xx.x, xx.y > 0 ? 0.0 : -1.0 + xx.y));
+    }
+  }
+  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) mn = fmin(mn, rp_candidate(x[m - 1], d, m - 1, d_scale));
+  mn = warp_min(mn);
+  if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
+}
+
 template <int G>
 __global__ void maxstep_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
                                  double d_scale, unsigned long long* key) {
@@ -324,7 +381,8 @@ int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling
   if (c.m == 0) return 0;
   nt_kind_kernel<<<(c.ncones + 255) / 256, 256, 0, st>>>(c, F, Fi);
   CIP_CHECK_LAUNCH();
-  nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
+  if (c.nq + c.ns == 0) nt_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, v, s, F, Fi, lambda);
+  else nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(nt_q_kernel, c, v, s, F, Fi, lambda);
   CIP_TRY(sdp_nt_scaling(c, F, Fi, v, s, lambda, info, st));
@@ -359,7 +417,8 @@ int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, c
 
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
-  prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
+  if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 0);
+  else prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(prod_q_kernel, c, x, y, o);
   CIP_TRY(sdp_prod_div(c, x, y, o, 0, st));
@@ -368,7 +427,8 @@ int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cu
 
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
-  prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
+  if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 1);
+  else prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(div_q_kernel, c, x, y, o);
   CIP_TRY(sdp_prod_div(c, x, y, o, 1, st));
@@ -382,7 +442,8 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
   maxstep_init_kernel<<<1, 1, 0, st>>>(key);
   CIP_CHECK_LAUNCH();
   if (c.m == 0) return 0;
-  maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
+  if (c.nq + c.ns == 0) maxstep_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, d, d_scale, key);
+  else maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(maxstep_q_kernel, c, x, d, d_scale, key);
   CIP_TRY(sdp_maxstep(c, x, d, d_scale, key, st));

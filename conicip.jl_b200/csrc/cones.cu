@@ -132,7 +132,10 @@ __global__ void nt_q_kernel(ConeDesc c, const double* __restrict__ v, const doub
   }
   wv = group_sum<G>(wv, sm);
   bib = group_sum<G>(bib, sm);
-  for (int i = lid; i < dim; i += G) lambda[off + i] = F.a[off + i] * z[i] + F.b[off + i] * wv;  // F*v
+  for (int i = lid; i < dim; i += G) {                             // lambda = F*v, w recomputed (no re-read)
+    const double w = (i == 0) ? w1 * scal : (inv2g * (sv[i] * irs - z[i] * irz)) * scal;
+    lambda[off + i] = ((i == 0) ? -beta : beta) * z[i] + w * wv;
+  }
   if (lid == 0) {
     F.D[ci] = 1.0;
     Fi.D[ci] = 1.0 / (-1.0 - bib);               // Z = inv(-inv(D) - B'X), D = 1
@@ -284,47 +287,60 @@ __global__ void maxstep_r_all_kernel(int m, const double* __restrict__ x, const 
   if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
 }
 
+// Grid-stride over the cones; every group keeps a running minimum and the CTA issues ONE atomicMin at
+// the end (half a million same-address atomics serialise in L2 and used to be the whole kernel time).
 template <int G>
 __global__ void maxstep_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
                                  double d_scale, unsigned long long* key) {
   __shared__ double sm[8];
-  int ci, off, dim, lid;
-  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
-  const double* xp = x + off;
-  double res;
-  if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
-    double nn = 0;
-    for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
-    nn = group_sum<G>(nn, sm);
-    const double al = sqrt(nn) - xp[0];
-    res = al < 0 ? 0.0 : -1.0 - al;
-  } else {                                                       // maxstep_soc(x, d), :242-262
-    const double* dp = d + off;
-    double xx = 0;
-    for (int i = lid; i < dim; i += G) xx += xp[i] * xp[i];
-    xx = group_sum<G>(xx, sm);
-    const double gam = 2 * xp[0] * xp[0] - xx;
-    const double irg = 1.0 / sqrt(gam), ids = -1.0 / d_scale;     // d <- -d / d_scale
-    const double d0 = dp[0] * ids;
-    double xd = 0;
-    for (int i = lid; i < dim; i += G) xd += (xp[i] * irg) * (dp[i] * ids);
-    xd = group_sum<G>(xd, sm);
-    const double xb0 = xp[0] * irg;
-    const double beta = 2 * xb0 * d0 - xd;
-    const double rho1 = beta * irg;
-    const double mu = (beta + d0) / (xb0 + 1);
-    double r2 = 0;
-    for (int i = lid; i < dim; i += G) {
-      if (i > 0) {
-        const double r = dp[i] * ids - mu * (xp[i] * irg);
-        r2 += r * r;
+  __shared__ double smin[8];
+  const int per_block = blockDim.x / G, lid = threadIdx.x % G;
+  const double ids = d ? -1.0 / d_scale : 0.0;                    // d <- -d / d_scale
+  double best = CUDART_INF;
+  for (int qi = blockIdx.x * per_block + threadIdx.x / G; qi < c.nq; qi += gridDim.x * per_block) {
+    const int ci = c.qlist[qi], off = c.off[ci], dim = c.off[ci + 1] - off;
+    const double* xp = x + off;
+    double res;
+    if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
+      double nn = 0;
+      for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
+      nn = group_sum<G>(nn, sm);
+      const double al = sqrt(nn) - xp[0];
+      res = al < 0 ? 0.0 : -1.0 - al;
+    } else {                                                       // maxstep_soc(x, d), :242-262
+      const double* dp = d + off;
+      double xx = 0, xdr = 0;
+      for (int i = lid; i < dim; i += G) { xx += xp[i] * xp[i]; }
+      xx = group_sum<G>(xx, sm);
+      const double gam = 2 * xp[0] * xp[0] - xx;
+      const double irg = 1.0 / sqrt(gam);
+      const double d0 = dp[0] * ids;
+      for (int i = lid; i < dim; i += G) xdr += (xp[i] * irg) * (dp[i] * ids);
+      const double xd = group_sum<G>(xdr, sm);
+      const double xb0 = xp[0] * irg;
+      const double beta = 2 * xb0 * d0 - xd;
+      const double rho1 = beta * irg;
+      const double mu = (beta + d0) / (xb0 + 1);
+      double r2 = 0;
+      for (int i = lid; i < dim; i += G) {
+        if (i > 0) {
+          const double r = dp[i] * ids - mu * (xp[i] * irg);
+          r2 += r * r;
+        }
       }
+      r2 = group_sum<G>(r2, sm);
+      const double al = sqrt(r2) * irg - rho1;
+      res = al < 0 ? CUDART_INF : 1.0 / al;
     }
-    r2 = group_sum<G>(r2, sm);
-    const double al = sqrt(r2) * irg - rho1;
-    res = al < 0 ? CUDART_INF : 1.0 / al;
+    best = fmin(best, res);
   }
-  if (lid == 0 && res < CUDART_INF) atomicMin(key, dkey(res));
+  // every lane of a group holds the same `best`; CTA minimum through shared memory
+  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmin(best, smin[w]);
+    if (best < CUDART_INF) atomicMin(key, dkey(best));
+  }
 }
 
 // ================================================================= scaled panel  Atil = F^-T A
@@ -384,7 +400,7 @@ int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling
   nt_kind_kernel<<<(c.ncones + 255) / 256, 256, 0, st>>>(c, F, Fi);
   CIP_CHECK_LAUNCH();
   if (c.nq + c.ns == 0) nt_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, v, s, F, Fi, lambda);
-  else nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
+  else if (c.nr_rows + c.ns > 0) nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(nt_q_kernel, c, v, s, F, Fi, lambda);
   CIP_TRY(sdp_nt_scaling(c, F, Fi, v, s, lambda, info, st));
@@ -420,7 +436,7 @@ int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, c
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
   if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 0);
-  else prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
+  else if (c.nr_rows > 0) prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(prod_q_kernel, c, x, y, o);
   CIP_TRY(sdp_prod_div(c, x, y, o, 0, st));
@@ -430,7 +446,7 @@ int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cu
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
   if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 1);
-  else prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
+  else if (c.nr_rows > 0) prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
   CIP_CHECK_LAUNCH();
   Q_DISPATCH(div_q_kernel, c, x, y, o);
   CIP_TRY(sdp_prod_div(c, x, y, o, 1, st));
@@ -445,9 +461,13 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
   CIP_CHECK_LAUNCH();
   if (c.m == 0) return 0;
   if (c.nq + c.ns == 0) maxstep_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, d, d_scale, key);
-  else maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
+  else if (c.nr_rows > 0) maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
   CIP_CHECK_LAUNCH();
-  Q_DISPATCH(maxstep_q_kernel, c, x, d, d_scale, key);
+  if (c.nq > 0) {
+    if (c.max_q_dim > 1024) maxstep_q_kernel<256><<<std::min(c.nq, 148 * 8), 256, 0, st>>>(c, x, d, d_scale, key);
+    else maxstep_q_kernel<32><<<std::min((c.nq + 7) / 8, 148 * 8), 256, 0, st>>>(c, x, d, d_scale, key);
+    CIP_CHECK_LAUNCH();
+  }
   CIP_TRY(sdp_maxstep(c, x, d, d_scale, key, st));
   return 0;
 }

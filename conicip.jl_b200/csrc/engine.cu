@@ -175,6 +175,7 @@ int form_H(cip_engine* h) {
     a.lower = 1; a.ntm = a.ntn = h->n_pad / TILE; a.sym = 1;
     a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = k_rows / 32;
     a.Cin = cin; a.Cout = h->H4; a.ldc = h->n_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
+    a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES;        // tall-skinny A (n << m): split the contraction
     CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, s));
   } else {
     if (cin) CIP_TRY(vec_copy(h->H4, cin, (size_t)h->n_pad * h->n_pad, s));
@@ -230,6 +231,7 @@ int factor_H(cip_engine* h) {
     a.lower = 1; a.ntm = a.ntn = ptiles; a.sym = 1;
     a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = h->n_pad / 32;
     a.Cin = h->Sbase4; a.Cout = h->S4; a.ldc = h->p_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
+    a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES;
     CIP_TRY(launch_gemm_nt(h->mapZ, h->mapZ, a, s));
     CIP_TRY(chol_factor(h->cholS, s));
   }
@@ -411,6 +413,9 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
   h->cd.row_cone = h->d_rowcone; h->cd.qlist = h->d_qlist; h->cd.nq = (int)qlist.size();
   h->cd.slist = h->d_slist; h->cd.ns = (int)slist.size(); h->cd.max_q_dim = maxq; h->cd.max_s_ord = maxs;
   h->cd.sord = h->d_sord; h->cd.roff = h->d_roff;
+  h->cd.nr_rows = 0;
+  for (int i = 0; i < ncones; ++i)
+    if (cone_type[i] == CIP_CONE_R) h->cd.nr_rows += h->h_off[i + 1] - h->h_off[i];
   for (Scaling* S : {&h->F, &h->Fi}) {
     CIP_TRY(dev_alloc(h, &S->kind, ncones));
     CIP_TRY(dev_alloc(h, &S->a, h->m_pad + 4));
@@ -436,6 +441,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
   CIP_TRY(dev_alloc(h, &h->Atil4, (size_t)(h->m_pad + h->aug_rows) * h->n_pad));
   CIP_TRY(dev_alloc(h, &h->Qq4, nn));
   CIP_TRY(dev_alloc(h, &h->H4, nn));
+  CIP_TRY(dev_alloc(h, &h->gemm_ws, (size_t)GEMM_WS_DOUBLES));
   CIP_TRY(dev_alloc(h, &h->Winv, (size_t)h->n_pad * TILE));
   CIP_TRY(dev_alloc(h, &h->info, 4));
   cudaStream_t s = h->stream;
@@ -583,7 +589,7 @@ int cip_destroy(cip_handle h) {
   }
   void* ptrs[] = {h->At4, h->Atil4, h->Qq4, h->H4, h->Winv, h->G4, h->Z4, h->S4, h->Sbase4, h->WinvS, h->info,
                   h->d_type, h->d_off, h->d_rowcone, h->d_qlist, h->d_slist, h->F.kind, h->F.a, h->F.b, h->F.D,
-                  h->Fi.kind, h->Fi.a, h->Fi.b, h->Fi.D, h->partial, h->scalar, h->F.R, h->F.Ri, h->d_sord, h->d_roff};
+                  h->Fi.kind, h->Fi.a, h->Fi.b, h->Fi.D, h->partial, h->scalar, h->F.R, h->F.Ri, h->d_sord, h->d_roff, h->gemm_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto v : h->nv) if (v) cudaFree(v);
   for (auto v : h->mv) if (v) cudaFree(v);

@@ -30,6 +30,7 @@ struct cip_engine {
   cip::ConeDesc cd{};
   cip::Scaling F{}, Fi{};
   bool have_scaling = false, have_factor = false;
+  double* gemm_ws = nullptr;   // split-K workspace of gemm_nt (GEMM_WS_DOUBLES)
   int aug_rows = 0;        // rows of Atil4 beyond m_pad holding sqrt(aug_rho) * G
   double aug_rho = 0.0;
   // work vectors

@@ -25,20 +25,11 @@ constexpr int BAND = 12;
 constexpr int NUM_THREADS = (CONSUMER_WARPS + 1) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-               const GemmArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  double* tiles = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8);
-  uint64_t* empty = full + STAGES;
-
-  int ti, tj;
+__device__ __forceinline__ void tile_of(const GemmArgs& a, int t, int& ti, int& tj) {
   if (a.lower) {
     // Band rasterisation of the lower-triangular tile grid: bands of BAND tile rows, column-major
     // inside a band, so the ~148 concurrently resident CTAs cover ~BAND rows x ~148/BAND columns and
     // share their X / Y panels in L2 (instead of one long row of tiles with 148 distinct Y panels).
-    const int t = blockIdx.x;
     int b = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f) / BAND;
     auto before = [](int bb) { const long long R = (long long)bb * BAND; return R * (R + 1) / 2; };
     while (before(b + 1) <= t) ++b;
@@ -58,9 +49,27 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ti = tj + local;
     }
   } else {
-    ti = blockIdx.x % a.ntm;
-    tj = blockIdx.x / a.ntm;
+    ti = t % a.ntm;
+    tj = t / a.ntm;
   }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+               const GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + STAGES;
+
+  int ti, tj;
+  // CTAs below tail0 own a whole tile; above it, ksplit consecutive CTAs share one (k tiles [kt0, kt1))
+  const bool split = (int)blockIdx.x >= a.tail0 && a.ksplit > 1;
+  const int tile = split ? a.tail0 + ((int)blockIdx.x - a.tail0) / a.ksplit : (int)blockIdx.x;
+  const int sp = split ? ((int)blockIdx.x - a.tail0) % a.ksplit : 0;
+  tile_of(a, tile, ti, tj);
+  const int kt0 = split ? sp * a.kchunk : 0;
+  const int kt1 = split ? ((kt0 + a.kchunk < a.nk) ? kt0 + a.kchunk : a.nk) : a.nk;
   const bool same = a.sym && (ti == tj);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -82,9 +91,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int xr = (a.x_row0 + ti * BM) * 4;
       const int yr = (a.y_row0 + tj * BN) * 4;
       const uint32_t bytes = same ? 2u * BOX_BYTES : 4u * BOX_BYTES;
-      for (int kt = 0; kt < a.nk; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int s = (kt - kt0) % STAGES;
+        const uint32_t ph = (uint32_t)((kt - kt0) / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         double* st = tiles + (size_t)s * STAGE_DOUBLES;
         mbar_arrive_expect_tx(&full[s], bytes);
@@ -111,9 +120,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int x_off = warp_m * BOX_DOUBLES + g * 4 + t;
   const int y_off = (same ? 0 : 2 * BOX_DOUBLES) + (warp_n >> 1) * BOX_DOUBLES + ((warp_n & 1) * 32 + g) * 4 + t;
 
-  for (int kt = 0; kt < a.nk; ++kt) {
-    const int s = kt % STAGES;
-    const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+  for (int kt = kt0; kt < kt1; ++kt) {
+    const int s = (kt - kt0) % STAGES;
+    const uint32_t ph = (uint32_t)((kt - kt0) / STAGES) & 1u;
     mbar_wait(&full[s], ph);
     const double* st = tiles + (size_t)s * STAGE_DOUBLES;
     const double* xs = st + x_off;
@@ -135,9 +144,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 
   // -------------------------------------------------------------- epilogue
+  const double alpha = a.alpha;
+  if (split) {
+    // partial tile -> workspace, tile-local Q4 (ld = 128); splitk_reduce_kernel finishes the job
+    double* wt = a.ws + (size_t)((int)blockIdx.x - a.tail0) * (size_t)(BM * BN);
+    const int lr = warp_m * 64 + g, lc = warp_n * 32 + 2 * t;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+        *reinterpret_cast<double2*>(wt + q4_index(lr + mi * 8, lc + ni * 8, BM)) =
+            make_double2(alpha * acc[mi][ni][0], alpha * acc[mi][ni][1]);
+    return;
+  }
   const int row_base = a.c_row0 + ti * BM + warp_m * 64 + g;
   const int col_base = a.c_col0 + tj * BN + warp_n * 32 + 2 * t;
-  const double alpha = a.alpha;
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int col = col_base + ni * 8;
@@ -151,6 +172,30 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       v.y += alpha * acc[mi][ni][1];
       *reinterpret_cast<double2*>(a.Cout + idx) = v;
     }
+  }
+}
+
+// C tile = Cin tile + sum over splits (in split order) of the partial tiles in the workspace
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs a) {
+  int ti, tj;
+  tile_of(a, a.tail0 + blockIdx.x, ti, tj);
+  const size_t slab = (size_t)(BM * BN);
+  const double* wt = a.ws + (size_t)blockIdx.x * a.ksplit * slab;
+  for (int e = threadIdx.x * 2; e < BM * BN; e += 512) {
+    double2 v = make_double2(0.0, 0.0);
+    for (int sp = 0; sp < a.ksplit; ++sp) {
+      const double2 w = *reinterpret_cast<const double2*>(wt + sp * slab + e);
+      v.x += w.x;
+      v.y += w.y;
+    }
+    const int quad = e / (BM * 4), lr = (e % (BM * 4)) >> 2, c = e & 3;
+    const size_t idx = q4_index(a.c_row0 + ti * BM + lr, a.c_col0 + tj * BN + quad * 4 + c, a.ldc);
+    if (a.Cin) {
+      const double2 ci = *reinterpret_cast<const double2*>(a.Cin + idx);
+      v.x += ci.x;
+      v.y += ci.y;
+    }
+    *reinterpret_cast<double2*>(a.Cout + idx) = v;
   }
 }
 
@@ -198,8 +243,34 @@ int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a
   }
   const long long tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
   if (tiles <= 0 || a.nk <= 0) return 0;
-  gemm_nt_kernel<<<(unsigned)tiles, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, a);
+  GemmArgs b = a;
+  b.ksplit = 1;
+  b.kchunk = a.nk;
+  b.tail0 = (int)tiles;
+  const long long tail = tiles % 148;
+  if (a.ws && tail > 0 && a.nk >= 8) {
+    // cost of the tail in units of one full tile: ceil(tail * ks / 148) / ks  (+ the reduction pass: a split
+    // costs about a quarter of one k tile); pick the cheapest ks that fits the workspace
+    const long long cap = a.ws_doubles / (long long)(BM * BN);
+    int best = 1;
+    double best_cost = 1.0;
+    for (int ks = 2; ks <= 148 && ks <= a.nk / 4 && tail * ks <= cap; ++ks) {
+      const double cost = (double)((tail * ks + 147) / 148) / ks + 0.25 * ks / a.nk;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+    }
+    if (best > 1) {
+      b.kchunk = (a.nk + best - 1) / best;
+      b.ksplit = (a.nk + b.kchunk - 1) / b.kchunk;                // no empty split
+      b.tail0 = (int)(tiles - tail);
+    }
+  }
+  const long long ctas = b.tail0 + (tiles - b.tail0) * b.ksplit;
+  gemm_nt_kernel<<<(unsigned)ctas, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, b);
   CIP_CHECK_LAUNCH();
+  if (b.ksplit > 1) {
+    splitk_reduce_kernel<<<(unsigned)(tiles - b.tail0), 256, 0, stream>>>(b);
+    CIP_CHECK_LAUNCH();
+  }
   return 0;
 }
 

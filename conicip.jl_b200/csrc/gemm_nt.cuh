@@ -30,7 +30,17 @@ struct GemmArgs {
   int ldc;             // Q4 ld of C
   int c_row0, c_col0;  // C origin
   double alpha;
+  // split-K tail.  The tile grid runs in waves of 148 CTAs; the tiles of the last, partial wave (all of
+  // them when the grid is smaller than one wave: tall-skinny products with a handful of C tiles and a
+  // very long contraction) are cut into `ksplit` contraction ranges so that the tail fills the SMs.
+  // Each tail CTA writes its partial tile to ws[((tile - tail0) * ksplit + split) * 128*128 ...] and a
+  // second kernel adds the partials in split order (deterministic) onto Cin.  Only used when `ws` is set.
+  double* ws;          // workspace, may be nullptr (never split)
+  long long ws_doubles;
+  int tail0;           // filled in by launch_gemm_nt: first split tile (CTAs below it contract all of K)
+  int ksplit, kchunk;  //   number of splits of a tail tile, k tiles per split
 };
+constexpr long long GEMM_WS_DOUBLES = 2048ll * 128 * 128;   // 2048 partial tiles (268 MB)
 
 // Creates a tensor map over a Q4 matrix (ld rows, kq_total quads).
 int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long kq_total);

@@ -44,6 +44,7 @@ struct ConeDesc {
   const int* slist;     // [ns] indices of S cones
   int ns;
   int max_q_dim;
+  int nr_rows;        // rows that belong to R cones
   int max_s_ord;
   const int* sord;      // [ns] matrix order k of every S cone (slist order)
   const int* roff;      // [ns] offset (in doubles) of its k*k block inside Scaling::R / Ri

@@ -62,7 +62,7 @@ def o_maxstep(cone_dims, x, d):
 
 
 # shapes chosen to hit: ragged n/m (not multiples of 128/32/4), p = 0 and p > 0, p > one tile, one
-# R row, many small Q cones, one large Q cone (CTA-per-cone path), cones straddling quads
+# R row, many small Q cones, one large Q cone (CTA-per-cone path), cones straddling quads, m >> n (split-K)
 CASES = {
     "mixed": dict(n=96, mr=80, ncones=6, k=9, p=5, seed=7),
     "ragged": dict(n=131, mr=77, ncones=3, k=33, p=0, seed=1),
@@ -71,6 +71,7 @@ CASES = {
     "one_big_q": dict(n=64, mr=1, ncones=1, k=2500, p=0, seed=6),
     "tiny": dict(n=1, mr=1, ncones=0, k=2, p=0, seed=8),
     "n_multi_tile": dict(n=520, mr=640, ncones=8, k=17, p=1, seed=9),
+    "tall_skinny": dict(n=200, mr=20000, ncones=40, k=33, p=3, seed=10),   # 3 C tiles, 667 k tiles: split-K SYRK
 }
 
 

@@ -3,6 +3,7 @@
 //                        L21  = A21 * inv(L11)'      -> gemm_nt (DMMA tiles)
 //                        A22 -= L21 * L21'           -> gemm_nt (lower, same tiles as the SYRK)
 // Replaces LAPACK qr/lu at src/kktsolvers.jl:35,:295 and the solves at :39-48,:299.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -12,7 +13,6 @@ namespace cip {
 
 namespace {
 constexpr int NB = 128;
-constexpr int SLD = 129;  // padded (odd) row stride of the shared 128x128 block: column walks are conflict-free
 
 __device__ __forceinline__ double fast_rcp(double d) {
   double x;
@@ -23,227 +23,366 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(x, e, x);
 }
 
-// Cholesky factor L and inverse inv(L) of one 128x128 diagonal block, one CTA of 512 threads.
-//   * four 32-column sub-panels; inside a sub-panel every thread keeps its 8 matrix elements in
-//     registers and only the current column travels through shared memory (double-buffered, one
-//     barrier per column); the pivot scaling is deferred (S[i][j] -= S[i][k] S[j][k] / d_k) so the
-//     dependent chain per column is LDS -> rcp -> FMA.  Rows below the 32x32 diagonal block are
-//     eliminated in the same sweep, i.e. the in-block TRSM comes for free.
-//   * rank-32 update of the remaining columns from a transposed copy of the sub-panel (4x4 register
-//     tiles, conflict-free 32-byte loads).
-//   * inv(L): the four 32x32 diagonal blocks by 4-lane column groups, then the off-diagonal blocks
-//     X_ij = -X_ii * sum_k L_ik X_kj by block distance.  X is kept transposed in the free upper
-//     triangle of S.
+// Cholesky factor L and inverse X = inv(L) of one 128x128 diagonal block, one CTA of 256 threads.
+// The block lives in shared memory column-major, Lc[c * LD + r] = L(r, c) for r >= c; the free triangle
+// (r < c) receives the strict lower triangle of X transposed, X(r, c) -> Lc[r * LD + c], and
+// X(r, r) = dinv[r].  LD = 132 makes every access pattern below conflict-free: lanes along r are
+// contiguous, and DMMA fragments (4 columns x 8 rows, or 8 columns x 4 rows) hit 16 distinct bank pairs
+// per half-warp.
+//   * four 32-column sub-panels.  Sweep: one thread per matrix row keeps its 32 sub-panel entries in
+//     registers.  The warp that owns the 32x32 diagonal block eliminates it alone (pivot by shuffle,
+//     column broadcast through a 32x32 scratch, __syncwarp only; scaling deferred so the chain per column
+//     is SHFL -> rcp -> FMA); one named barrier later the warps below apply the 32 published columns
+//     to their rows without further synchronisation (the in-block TRSM).
+//   * rank-32 update of the trailing columns on the tensor pipe: 16x16 blocks per warp, DMMA.8x8x4
+//     fragments read straight from the column-major block.
+//   * inv(L): the four diagonal 32x32 blocks by one warp each (thread = column, forward substitution
+//     in registers against broadcast reads of L), then the off-diagonal blocks
+//     X_ij = -X_ii * sum_k L_ik X_kj by block distance as 8x8 DMMA tiles.
 constexpr int SB = 32;           // sub-panel width
-constexpr int PLD = 132;         // leading dimension of the transposed sub-panel copy P[k][i]
-constexpr int SWEEP_WARPS = 16;  // warps that run the column sweep of a sub-panel (8 was measured slower: 118 vs 112 us)
-constexpr int SWEEP_ROWS = NB / SWEEP_WARPS;   // matrix elements per thread during the sweep
+constexpr int LD = 132;          // column stride of the shared block
+constexpr int TLD = 36;          // row stride of the 32x32 T blocks of the inverse
+constexpr int PT = 256;          // threads of potrf_diag_kernel: 8 warps, so that a thread may hold ~250 registers (row + load batch)
+constexpr int PW = PT / 32;
+constexpr int POTRF_SMEM = (NB * LD + NB + SB * SB + 2 * SB + 3 * SB * TLD) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(512, 1)
+// X(rr, cc) of the (partially built) inverse: strict lower part from the free triangle, diagonal from dinv
+__device__ __forceinline__ double xinv_at(const double* Lc, const double* dinv, int rr, int cc) {
+  // both loads unconditional (any (rr, cc) is inside the block), the choice is a select: lanes of a DMMA
+  // fragment straddle the diagonal and must not diverge
+  const double v = Lc[rr * LD + cc], dv = dinv[rr];
+  return rr > cc ? v : (rr == cc ? dv : 0.0);
+}
+
+// Off-diagonal blocks of the inverse at block distance DLT: X(b+DLT, b) = -X(b+DLT, b+DLT) T_b with
+// T_b = sum_{kb = b .. b+DLT-1} L(b+DLT, kb) X(kb, b).  A 32x32 block is 16 tiles of 8x8; warp w owns the
+// tiles (tr, tc) = (w >> 2, w & 3) and (tr + 2, tc) of every block and advances all of them together, one
+// DMMA each per k step, so that the dependent-DMMA latency of one tile is hidden by the others.
+template <int DLT>
+__device__ __forceinline__ void inv_offdiag(double* Lc, const double* dinv, double* T, int w, int g, int t4) {
+  constexpr int NT = 2 * (NB / SB - DLT);        // tiles of this warp
+  const int tc = w & 3, tr0 = w >> 2;
+  double c0v[NT], c1v[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) c0v[i] = c1v[i] = 0.0;
+  // rows of X(., cj..cj+7) above cj are zero: the first k block starts at step 2 tc
+#pragma unroll 2
+  for (int st = 2 * tc; st < DLT * 8; ++st) {
+    double av[NT], bv[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int b = i >> 1, tr = tr0 + 2 * (i & 1);
+      const int kk = b * SB + 4 * st + t4;
+      av[i] = Lc[kk * LD + (b + DLT) * SB + 8 * tr + g];
+      bv[i] = (st < 8) ? xinv_at(Lc, dinv, kk, b * SB + 8 * tc + g) : Lc[kk * LD + b * SB + 8 * tc + g];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) dmma884(c0v[i], c1v[i], av[i], bv[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int b = i >> 1, tr = tr0 + 2 * (i & 1);
+    *reinterpret_cast<double2*>(T + (b * SB + 8 * tr + g) * TLD + 8 * tc + 2 * t4) = make_double2(c0v[i], c1v[i]);
+    c0v[i] = c1v[i] = 0.0;
+  }
+  __syncthreads();
+  // X_ii is lower triangular: tile row tr needs k < 8 tr + 8
+#pragma unroll
+  for (int st = 0; st < 8; ++st) {
+    double av[NT], bv[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int b = i >> 1, tr = tr0 + 2 * (i & 1), i0 = (b + DLT) * SB;
+      av[i] = xinv_at(Lc, dinv, i0 + 8 * tr + g, i0 + 4 * st + t4);
+      bv[i] = T[(b * SB + 4 * st + t4) * TLD + 8 * tc + g];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+      if (st < 2 * (tr0 + 2 * (i & 1)) + 2) dmma884(c0v[i], c1v[i], av[i], bv[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const int b = i >> 1, tr = tr0 + 2 * (i & 1), i0 = (b + DLT) * SB;
+    *reinterpret_cast<double2*>(Lc + (i0 + 8 * tr + g) * LD + b * SB + 8 * tc + 2 * t4) = make_double2(-c0v[i], -c1v[i]);
+  }
+  __syncthreads();
+}
+
+#ifdef CIP_POTRF_PROF
+#define PROF_MARK(i) do { prof_t[i] = clock64(); } while (0)
+#else
+#define PROF_MARK(i) do { } while (0)
+#endif
+
+// Row application a[j] -= tt * row[j] for j in (K, 32), `row` being a broadcast row of 32 doubles in
+// shared memory.  The loads are issued as one batch of 16-byte loads ahead of the arithmetic (with one
+// warp per scheduler nothing else hides the LDS latency), split from the FMAs so that the caller can
+// put the pivot reciprocal chain between the two.
+template <int K>
+struct RowBatch {
+  static constexpr int P0 = (K + 1) >> 1;          // first pair that holds an index > K
+  double2 u[16 - P0 > 0 ? 16 - P0 : 1];
+  __device__ __forceinline__ void load(const double* row) {
+    const double2* r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+    for (int p = P0; p < 16; ++p) u[p - P0] = r2[p];
+  }
+  __device__ __forceinline__ double first() const { return ((K + 1) & 1) ? u[0].y : u[0].x; }   // row[K + 1]
+  __device__ __forceinline__ void apply_rest(double (&a)[SB], double tt) const {                 // j >= K + 2
+#pragma unroll
+    for (int p = P0; p < 16; ++p) {
+      if (2 * p > K + 1) a[2 * p] = fma(-tt, u[p - P0].x, a[2 * p]);
+      if (2 * p + 1 > K + 1) a[2 * p + 1] = fma(-tt, u[p - P0].y, a[2 * p + 1]);
+    }
+  }
+  __device__ __forceinline__ void apply(double (&a)[SB], double tt) const {
+#pragma unroll
+    for (int p = P0; p < 16; ++p) {
+      if (2 * p > K) a[2 * p] = fma(-tt, u[p - P0].x, a[2 * p]);
+      a[2 * p + 1] = fma(-tt, u[p - P0].y, a[2 * p + 1]);
+    }
+  }
+};
+// One column of the diagonal 32x32 block (warp-synchronous).  On entry column K is already published
+// (Bs[K][lane] = a[K]) and `d` is its pivot; the stage finishes the next column first and publishes it
+// before touching the other 30 entries, so the dependent chain per column is
+// SHFL -> MUFU.RCP64H -> 3 DFMA -> DFMA.  The reciprocal is never formed on the chain:
+// a[K] / d = t0 (1 + e + e^2) with r0 ~ 1/d to 20 bits, t0 = a[K] r0, e = 1 - d r0  (|e|^3 < 2^-60).
+template <int K>
+struct DiagSweep {
+  static __device__ __forceinline__ void run(double (&a)[SB], double* Bs, double* rd, double& dj, int& badcol, int lane,
+                                             double d) {
+    __syncwarp();
+    RowBatch<K> rb;
+    rb.load(Bs + K * SB);
+    const bool bad = !(d > 0.0);
+    badcol = (bad && badcol == 0) ? K + 1 : badcol;
+    d = bad ? 1.0 : d;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double e = fma(-d, r0, 1.0), t0 = a[K] * r0;
+    const double pp = fma(e, e, e);
+    const double tt = fma(t0, pp, t0);
+    double dn = 0.0;
+    if (K + 1 < SB) {
+      a[(K + 1) % SB] = fma(-tt, rb.first(), a[(K + 1) % SB]);
+      Bs[((K + 1) % SB) * SB + lane] = a[(K + 1) % SB];
+      dn = __shfl_sync(0xffffffffu, a[(K + 1) % SB], (K + 1) % SB);
+    }
+    if (lane == K) { dj = d; rd[K] = fma(r0, pp, r0); }
+    rb.apply_rest(a, tt);
+    DiagSweep<K + 1>::run(a, Bs, rd, dj, badcol, lane, dn);
+  }
+};
+template <>
+struct DiagSweep<SB> {
+  static __device__ __forceinline__ void run(double (&)[SB], double*, double*, double&, int&, int, double) {}
+};
+template <int K>
+struct BelowSweep {
+  static __device__ __forceinline__ void run(double (&a)[SB], const double* Bs, const double* rd) {
+    RowBatch<K> rb;
+    rb.load(Bs + K * SB);
+    rb.apply(a, a[K] * rd[K]);
+    BelowSweep<K + 1>::run(a, Bs, rd);
+  }
+};
+template <>
+struct BelowSweep<SB> {
+  static __device__ __forceinline__ void run(double (&)[SB], const double*, const double*) {}
+};
+
+
+__global__ void __launch_bounds__(PT, 1)
 potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W, int* info) {
-  extern __shared__ double S[];                  // S[r * SLD + c]
-  double* dinv = S + NB * SLD;                   // [NB]   1 / L_kk
-  double* colk = dinv + NB;                      // [2][NB] travelling column (double-buffered)
-  double* P = colk + 2 * NB;                     // [SB][PLD] transposed sub-panel; later block temporaries
+  extern __shared__ __align__(16) double Lc[];   // Lc[c * LD + r]
+  double* dinv = Lc + NB * LD;                   // [NB]      1 / L_kk
+  double* Bs = dinv + NB;                        // [SB][SB]  unscaled diagonal block of the sub-panel, Bs[k][j] = S(c0+j, c0+k)
+  double* rd = Bs + SB * SB;                     // [SB]      1 / d_k   (pivot reciprocals)
+  double* rsq = rd + SB;                         // [SB]      1 / sqrt(d_k)
+  double* T = rsq + SB;                          // [3][SB][TLD] block temporaries of the inverse
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;        // DMMA fragment coordinates
+#ifdef CIP_POTRF_PROF
+  long long prof_t[16];
+#endif
+  PROF_MARK(0);
   {
     const int r = tid & 127;
-    for (int q = tid >> 7; q < 32; q += 4) {
+    for (int q = tid >> 7; q < 32; q += PT / 128) {
+      if (4 * q > r) continue;                   // strictly-upper quads are never read
       const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + q) * ld + j0 + r) * 4);
       const double2 v0 = p[0], v1 = p[1];
-      double* d = S + r * SLD + 4 * q;
-      d[0] = v0.x; d[1] = v0.y; d[2] = v1.x; d[3] = v1.y;
+      Lc[(4 * q + 0) * LD + r] = v0.x;
+      Lc[(4 * q + 1) * LD + r] = v0.y;
+      Lc[(4 * q + 2) * LD + r] = v1.x;
+      Lc[(4 * q + 3) * LD + r] = v1.y;
     }
   }
   __syncthreads();
+  PROF_MARK(1);
 
-  for (int c0 = 0; c0 < NB; c0 += SB) {
-    // ---- sub-panel sweep (column j = c0 + lane, rows i_e = w + SWEEP_WARPS e): the per-column chain is
-    //      update -> publish -> barrier -> pivot reciprocal, so elements per thread are kept small.
-    if (w < SWEEP_WARPS) {
-      const int j = c0 + lane;
-      double a[SWEEP_ROWS];
+  for (int s = 0; s < NB / SB; ++s) {
+    const int c0 = s * SB;
+    // ---- sub-panel sweep: thread = row i (warps 0..3), a[j] = S(i, c0 + j)
+    if (w < NB / SB && w >= s) {
+      const int i = tid;
+      double a[SB];
 #pragma unroll
-      for (int e = 0; e < SWEEP_ROWS; ++e) {
-        const int i = w + SWEEP_WARPS * e;
-        a[e] = (i >= j) ? S[i * SLD + j] : 0.0;
+      for (int j = 0; j < SB; ++j) {
+        const double v = Lc[(c0 + j) * LD + i];     // unconditional load + select: no divergence in the diagonal warp
+        a[j] = (c0 + j <= i) ? v : 0.0;
       }
-      double dj = 1.0;
-      for (int k = 0; k < SB; ++k) {
-        double* ck = colk + (k & 1) * NB;
-        if (lane == k) {
+#ifdef CIP_POTRF_PROF
+      long long q0 = clock64(), q1 = 0, q2 = 0, q3 = 0;
+#endif
+      if (w == s) {
+        // the diagonal 32x32 block, warp-synchronous
+        double dj = 1.0;
+        int badcol = 0;
+        Bs[lane] = a[0];
+        DiagSweep<0>::run(a, Bs, rd, dj, badcol, lane, __shfl_sync(0xffffffffu, a[0], 0));
+        if (badcol && lane == 0) atomicCAS(info, 0, j0 + c0 + badcol);
+#ifdef CIP_POTRF_PROF
+        q1 = clock64();
+#endif
+        const double rs = 1.0 / sqrt(dj);
+        rsq[lane] = rs;
+        dinv[c0 + lane] = rs;
+        a[0] = (lane == 0) ? dj : a[0];          // diagonal entry: d_j / sqrt(d_j); set per lane below
 #pragma unroll
-          for (int e = 0; e < SWEEP_ROWS; ++e) ck[w + SWEEP_WARPS * e] = a[e];
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_WARPS * 32) : "memory");
-        double d = ck[c0 + k];
-        const bool bad = !(d > 0.0);
-        if (bad && tid == 0) atomicCAS(info, 0, j0 + c0 + k + 1);
-        d = bad ? 1.0 : d;
-        if (lane == k) dj = d;
-        if (lane > k) {
-          const double t = ck[j] * fast_rcp(d);
-#pragma unroll
-          for (int e = 0; e < SWEEP_ROWS; ++e) {
-            const int i = w + SWEEP_WARPS * e;
-            if (i >= j) a[e] = fma(-ck[i], t, a[e]);
-          }
-        }
+        for (int j = 1; j < SB; ++j) a[j] = (lane == j) ? dj : a[j];
       }
-      // scale: L[i][j] = a / sqrt(d_j); publish to S and to the transposed copy P[lane][i]
-      const double rs = 1.0 / sqrt(dj);
-      if (w == (j & (SWEEP_WARPS - 1))) dinv[j] = rs;     // exactly one thread per column (the owner of (j,j))
-#pragma unroll
-      for (int e = 0; e < SWEEP_ROWS; ++e) {
-        const int i = w + SWEEP_WARPS * e;
-        double v = 0.0;
-        if (i > j) v = a[e] * rs;
-        else if (i == j) v = dj * rs;
-        if (i >= c0) {
-          S[i * SLD + j] = v;
-          P[lane * PLD + i] = v;
-        }
+      asm volatile("bar.sync 1, %0;" ::"r"((NB / SB - s) * 32) : "memory");
+#ifdef CIP_POTRF_PROF
+      q2 = clock64();
+#endif
+      if (w > s) {
+        // rows below the diagonal block: apply the 32 published columns (no further synchronisation)
+        BelowSweep<0>::run(a, Bs, rd);
       }
+#ifdef CIP_POTRF_PROF
+      q3 = clock64();
+      if (lane == 0 && j0 == 256 && CIP_POTRF_PROF > 1) printf("  s=%d w=%d: load+diag %lld | sqrt+bar %lld | below %lld (t0 %lld)\n", s, w, q1 ? q1 - q0 : 0, q2 - (q1 ? q1 : q0), q3 - q2, q0 - prof_t[0]);
+#endif
+      // L(i, c0 + j) = a[j] / sqrt(d_j)
+#pragma unroll
+      for (int j = 0; j < SB; ++j)
+        if (c0 + j <= i) Lc[(c0 + j) * LD + i] = a[j] * rsq[j];
     }
     __syncthreads();
-    // ---- rank-32 update of the columns right of the sub-panel: 4x4 register tiles, lower part
-    const int R = NB - c0 - SB;                    // remaining order
-    if (R > 0) {
-      const int nt4 = R / 4;
-      const int ntile = nt4 * (nt4 + 1) / 2;
-      for (int t = tid; t < ntile; t += 512) {
-        int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        while (ti * (ti + 1) / 2 > t) --ti;
-        const int tj = t - ti * (ti + 1) / 2;
-        const int i0 = c0 + SB + 4 * ti, jj0 = c0 + SB + 4 * tj;
-        double acc[4][4];
+    PROF_MARK(2 + 2 * s);
+    // ---- rank-32 update of the trailing columns, lower 16x16 blocks, DMMA
+    const int base = c0 + SB;
+    const int nb16 = (NB - base) / 16;
+    const int nblk = nb16 * (nb16 + 1) / 2;
+    for (int blk = w; blk < nblk; blk += PW) {
+      int bi = 0, bj = blk;
+      while (bj > bi) { bj -= bi + 1; ++bi; }
+      const int i0 = base + 16 * bi, jj0 = base + 16 * bj;
+      double acc[2][2][2];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < 2; ++x)
 #pragma unroll
-          for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < SB; ++k) {
-          const double2 p0 = *reinterpret_cast<const double2*>(P + k * PLD + i0);
-          const double2 p1 = *reinterpret_cast<const double2*>(P + k * PLD + i0 + 2);
-          const double2 q0 = *reinterpret_cast<const double2*>(P + k * PLD + jj0);
-          const double2 q1 = *reinterpret_cast<const double2*>(P + k * PLD + jj0 + 2);
-          const double li[4] = {p0.x, p0.y, p1.x, p1.y}, lj[4] = {q0.x, q0.y, q1.x, q1.y};
+        for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = fma(li[x], lj[y], acc[x][y]);
-        }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y)
-            if (i0 + x >= jj0 + y) S[(i0 + x) * SLD + jj0 + y] -= acc[x][y];
+      for (int kq = 0; kq < SB / 4; ++kq) {
+        const double* colp = Lc + (c0 + 4 * kq + t4) * LD;
+        const double a0 = colp[i0 + g], a1 = colp[i0 + 8 + g];
+        const double b0 = colp[jj0 + g], b1 = colp[jj0 + 8 + g];
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
       }
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          const int row = i0 + 8 * x + g, col = jj0 + 8 * y + 2 * t4;
+          if (row >= col) Lc[col * LD + row] -= acc[x][y][0];
+          if (row >= col + 1) Lc[(col + 1) * LD + row] -= acc[x][y][1];
+        }
     }
     __syncthreads();
+    PROF_MARK(3 + 2 * s);
   }
 
-  // ---- write L back (strict upper triangle as zeros)
+  // ---- write L back: the quads up to the diagonal (zeros right of it inside the last one; the quads
+  //      beyond are never read by anyone).  Only reads the lower triangle, so it needs no barrier
+  //      against the inverse below, which writes the free triangle
   {
     const int r = tid & 127;
-    for (int q = tid >> 7; q < 32; q += 4) {
+    for (int q = tid >> 7; q < 32; q += PT / 128) {
+      if (4 * q > r) continue;
       double o[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) o[t] = (4 * q + t > r) ? 0.0 : S[r * SLD + 4 * q + t];
+      for (int t = 0; t < 4; ++t) o[t] = (4 * q + t > r) ? 0.0 : Lc[(4 * q + t) * LD + r];
       double2* p = reinterpret_cast<double2*>(H + ((size_t)(j0 / 4 + q) * ld + j0 + r) * 4);
       p[0] = make_double2(o[0], o[1]);
       p[1] = make_double2(o[2], o[3]);
     }
   }
-  __syncthreads();
+  PROF_MARK(10);
 
-  // ---- inverse.  X(r,c), r > c, lives at S[c][r]; X(r,r) = dinv[r].
-#define XG(r, c) S[(c) * SLD + (r)]
-  {
-    // diagonal 32x32 blocks: 4 blocks x 32 columns x 4 lanes = 512 threads, no block barrier.  All
-    // groups of a warp walk the same row index i (columns that start later are predicated off), so
-    // the warp stays convergent instead of serialising eight 4-lane paths.
-    const int blk = tid >> 7, jl = (tid & 127) >> 2, part = tid & 3;
-    const int b0 = blk * SB, jc = b0 + jl;
-    const double xjj = dinv[jc];
-    for (int i = b0 + 1; i < b0 + SB; ++i) {
-      const bool active = i > jc;
-      const double* Li = S + i * SLD;
-      double s0 = 0.0, s1 = 0.0;
-      if (active) {
-        if (part == 0) s0 = Li[jc] * xjj;
-        int k = jc + 1 + part;
-        for (; k + 4 < i; k += 8) {
-          s0 = fma(Li[k], XG(k, jc), s0);
-          s1 = fma(Li[k + 4], XG(k + 4, jc), s1);
-        }
-        if (k < i) s0 = fma(Li[k], XG(k, jc), s0);
-      }
-      double sum = s0 + s1;
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      if (active && part == 0) XG(i, jc) = -sum * dinv[i];
-      __syncwarp();
+  // ---- inverse, diagonal 32x32 blocks: warp b, lane = column.  x[i] first accumulates
+  //      sum_k L(i, k) X(k, j), then becomes X(i, j) = -x[i] / L(i, i).
+  if (w < NB / SB) {
+    const int b0 = w * SB;
+    double x[SB];
+#pragma unroll
+    for (int i = 0; i < SB; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SB; ++k) {
+      const double dk = dinv[b0 + k];
+      x[k] = (k < lane) ? 0.0 : ((k == lane) ? dk : -dk * x[k]);
+      const double* col = Lc + (b0 + k) * LD + b0;               // L(b0 + i, b0 + k), broadcast reads
+#pragma unroll
+      for (int i = k + 1; i < SB; ++i) x[i] = fma(col[i], x[k], x[i]);
     }
+#pragma unroll
+    for (int i = 1; i < SB; ++i)
+      if (i > lane) Lc[(b0 + i) * LD + b0 + lane] = x[i];
   }
   __syncthreads();
-  for (int dlt = 1; dlt < NB / SB; ++dlt) {
-    const int nblk = NB / SB - dlt;
-    // T_b = sum_{kk} L(ib, kk) * X(kk, jb)   for block pairs (ib, jb) = (b + dlt, b)
-    for (int o = tid; o < nblk * SB * SB; o += 512) {
-      const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
-      const int ri = (b + dlt) * SB + r, cj = b * SB + c;
-      const double* Li = S + ri * SLD;
-      // four independent partial sums: the dependent-FMA chain, not the loads, bounds this loop
-      double s0 = Li[cj] * dinv[cj], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* Xc = S + cj * SLD;                      // XG(kk, cj) = Xc[kk]
-      const int kend = (b + dlt) * SB;
-      int kk = cj + 1;
-      for (; kk + 3 < kend; kk += 4) {
-        s0 = fma(Li[kk], Xc[kk], s0);
-        s1 = fma(Li[kk + 1], Xc[kk + 1], s1);
-        s2 = fma(Li[kk + 2], Xc[kk + 2], s2);
-        s3 = fma(Li[kk + 3], Xc[kk + 3], s3);
-      }
-      for (; kk < kend; ++kk) s0 = fma(Li[kk], Xc[kk], s0);
-      P[(b * SB + r) * SB + c] = (s0 + s1) + (s2 + s3);
-    }
-    __syncthreads();
-    // X_ib,jb = - X_ib,ib * T_b
-    for (int o = tid; o < nblk * SB * SB; o += 512) {
-      const int b = o / (SB * SB), r = (o / SB) % SB, c = o % SB;
-      const int i0 = (b + dlt) * SB;
-      double s0 = dinv[i0 + r] * P[(b * SB + r) * SB + c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* Pc = P + (b * SB) * SB + c;             // Pc[k * SB] = T_b[k][c]
-      int k = 0;
-      for (; k + 3 < r; k += 4) {
-        s0 = fma(XG(i0 + r, i0 + k), Pc[k * SB], s0);
-        s1 = fma(XG(i0 + r, i0 + k + 1), Pc[(k + 1) * SB], s1);
-        s2 = fma(XG(i0 + r, i0 + k + 2), Pc[(k + 2) * SB], s2);
-        s3 = fma(XG(i0 + r, i0 + k + 3), Pc[(k + 3) * SB], s3);
-      }
-      for (; k < r; ++k) s0 = fma(XG(i0 + r, i0 + k), Pc[k * SB], s0);
-      XG(i0 + r, b * SB + c) = -((s0 + s1) + (s2 + s3));
-    }
-    __syncthreads();
-  }
+  PROF_MARK(11);
+  // ---- inverse, off-diagonal blocks by block distance (inv_offdiag below)
+  inv_offdiag<1>(Lc, dinv, T, w, g, t4);
+  PROF_MARK(12);
+  inv_offdiag<2>(Lc, dinv, T, w, g, t4);
+  PROF_MARK(13);
+  inv_offdiag<3>(Lc, dinv, T, w, g, t4);
+  PROF_MARK(14);
   {
-    // W[r][c] = X(r,c) = (c < r) ? S[c][r] : (c == r ? dinv[r] : 0)
+    // W[r][c] = X(r, c); quads right of the diagonal stay zero (the buffer is zero-initialised and only
+    // this kernel, or a broadcast of its output, ever writes it)
     const int r = tid & 127;
-    for (int q = tid >> 7; q < 32; q += 4) {
-      double o[4];
+    for (int q = tid >> 7; q < 32; q += PT / 128) {
+      if (4 * q > r) continue;
+      const double2 x0 = *reinterpret_cast<const double2*>(Lc + r * LD + 4 * q);
+      const double2 x1 = *reinterpret_cast<const double2*>(Lc + r * LD + 4 * q + 2);
+      double o[4] = {x0.x, x0.y, x1.x, x1.y};
+      if (4 * q + 3 >= r) {                       // the quad that holds the diagonal
+        const double dr = dinv[r];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int cc = 4 * q + t;
-        o[t] = (cc < r) ? S[cc * SLD + r] : ((cc == r) ? dinv[r] : 0.0);
+        for (int t = 0; t < 4; ++t) o[t] = (4 * q + t < r) ? o[t] : ((4 * q + t == r) ? dr : 0.0);
       }
       double2* p = reinterpret_cast<double2*>(W + ((size_t)q * NB + r) * 4);
       p[0] = make_double2(o[0], o[1]);
       p[1] = make_double2(o[2], o[3]);
     }
   }
-#undef XG
+#ifdef CIP_POTRF_PROF
+  __syncthreads();
+  PROF_MARK(15);
+  if (tid == 0 && j0 == 256) {
+    printf("potrf prof (cycles): load %lld |", prof_t[1] - prof_t[0]);
+    for (int i = 0; i < 4; ++i) printf(" sweep%d %lld upd%d %lld |", i, prof_t[2 + 2 * i] - prof_t[1 + 2 * i], i, prof_t[3 + 2 * i] - prof_t[2 + 2 * i]);
+    printf(" writeL %lld | invdiag %lld | inv1 %lld inv2 %lld inv3 %lld | writeW %lld | total %lld\n", prof_t[10] - prof_t[9],
+           prof_t[11] - prof_t[10], prof_t[12] - prof_t[11], prof_t[13] - prof_t[12], prof_t[14] - prof_t[13], prof_t[15] - prof_t[14],
+           prof_t[15] - prof_t[0]);
+  }
+#endif
 }
 
 // forward sweep step for panel jb:  y_j = inv(L_jj) b_j ;  b_i -= L_ij y_j  (i > j)
@@ -388,7 +527,7 @@ void chol_free_plan(CholPlan* p) {
 //   high-priority stream `sc`, so its factorisation overlaps the bulk update running on `s`.
 int chol_factor(const CholPlan& p, cudaStream_t s) {
   constexpr int OUTER = 4;
-  const int smem = (NB * SLD + 3 * NB + SB * PLD) * (int)sizeof(double);
+  const int smem = POTRF_SMEM;
   if (!g_potrf_attr) {
     CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     g_potrf_attr = true;
@@ -403,7 +542,7 @@ int chol_factor(const CholPlan& p, cudaStream_t s) {
     const int J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
     for (int jb = J0; jb < J1; ++jb) {
       const int j0 = jb * NB;
-      potrf_diag_kernel<<<1, 512, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
+      potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
       CIP_CHECK_LAUNCH();
       const int rem = np - jb - 1;
       if (rem == 0) break;
@@ -458,7 +597,7 @@ int factor_outer_panel(const CholPlan& p, int J0, int J1, cudaStream_t sc, int s
   const int np = p.npanels;
   for (int jb = J0; jb < J1; ++jb) {
     const int j0 = jb * NB;
-    potrf_diag_kernel<<<1, 512, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
+    potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
     CIP_CHECK_LAUNCH();
     const int rem = np - jb - 1;
     if (rem == 0) break;
@@ -497,7 +636,7 @@ int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
   if (const char* env = getenv("CIP_DIST_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
   const NcclApi* api = nccl_api();
   if (!api) return -1;
-  const int smem = (NB * SLD + 3 * NB + SB * PLD) * (int)sizeof(double);
+  const int smem = POTRF_SMEM;
   if (!g_potrf_attr) {
     CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     g_potrf_attr = true;

@@ -23,6 +23,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(x, e, x);
 }
 
+// 1 / sqrt(d), branch-free (the IEEE sqrt and division sequences carry slow-path branches that cut the
+// instruction stream of the sweep into pieces): 20-bit seed, one third-order step, |e|^3 < 2^-60.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d * y, y, 1.0);
+  const double p = fma(0.375, e, 0.5) * e;
+  return fma(y, p, y);
+}
+
 // Cholesky factor L and inverse X = inv(L) of one 128x128 diagonal block, one CTA of 256 threads.
 // The block lives in shared memory column-major, Lc[c * LD + r] = L(r, c) for r >= c; the free triangle
 // (r < c) receives the strict lower triangle of X transposed, X(r, c) -> Lc[r * LD + c], and
@@ -44,7 +54,7 @@ constexpr int LD = 132;          // column stride of the shared block
 constexpr int TLD = 36;          // row stride of the 32x32 T blocks of the inverse
 constexpr int PT = 256;          // threads of potrf_diag_kernel: 8 warps, so that a thread may hold ~250 registers (row + load batch)
 constexpr int PW = PT / 32;
-constexpr int POTRF_SMEM = (NB * LD + NB + SB * SB + 2 * SB + 3 * SB * TLD) * (int)sizeof(double);
+constexpr int POTRF_SMEM = (NB * LD + NB + 2 * (SB * SB + 2 * SB) + 3 * SB * TLD) * (int)sizeof(double);
 
 // X(rr, cc) of the (partially built) inverse: strict lower part from the free triangle, diagonal from dinv
 __device__ __forceinline__ double xinv_at(const double* Lc, const double* dinv, int rr, int cc) {
@@ -52,6 +62,48 @@ __device__ __forceinline__ double xinv_at(const double* Lc, const double* dinv, 
   // fragment straddle the diagonal and must not diverge
   const double v = Lc[rr * LD + cc], dv = dinv[rr];
   return rr > cc ? v : (rr == cc ? dv : 0.0);
+}
+
+// Look-ahead part of the rank-32 update: the 32x32 diagonal block (s, s) right of the sub-panel at c0, as ten
+// lower 8x8 tiles t = idx, idx + nw (< 10), both advanced together.
+__device__ __forceinline__ void own_block_update(double* Lc, int c0, int idx, int nw, int g, int t4) {
+  const int base = c0 + SB;
+  int tr[2], tc[2];
+  bool on[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = idx + u * nw;
+    on[u] = t < 10;
+    int r = 0, c = on[u] ? t : 0;
+    while (c > r) { c -= r + 1; ++r; }
+    tr[u] = r; tc[u] = c;
+  }
+  double av[2][SB / 4], bv[2][SB / 4], c0v[2] = {0.0, 0.0}, c1v[2] = {0.0, 0.0};
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int kq = 0; kq < SB / 4; ++kq) {
+      const double* colp = Lc + (c0 + 4 * kq + t4) * LD + base + g;
+      av[u][kq] = colp[8 * tr[u]];
+      bv[u][kq] = colp[8 * tc[u]];
+    }
+#pragma unroll
+  for (int kq = 0; kq < SB / 4; ++kq)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) dmma884(c0v[u], c1v[u], av[u][kq], bv[u][kq]);
+  double cv[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int row = base + 8 * tr[u] + g, col = base + 8 * tc[u] + 2 * t4;
+    cv[u][0] = Lc[col * LD + row];
+    cv[u][1] = Lc[(col + 1) * LD + row];
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int row = base + 8 * tr[u] + g, col = base + 8 * tc[u] + 2 * t4;
+    if (on[u] && row >= col) Lc[col * LD + row] = cv[u][0] - c0v[u];
+    if (on[u] && row >= col + 1) Lc[(col + 1) * LD + row] = cv[u][1] - c1v[u];
+  }
 }
 
 // Off-diagonal blocks of the inverse at block distance DLT: X(b+DLT, b) = -X(b+DLT, b+DLT) T_b with
@@ -110,8 +162,10 @@ __device__ __forceinline__ void inv_offdiag(double* Lc, const double* dinv, doub
 
 #ifdef CIP_POTRF_PROF
 #define PROF_MARK(i) do { prof_t[i] = clock64(); } while (0)
+#define DBG_MARK(s, k) do { if (lane == 0) dbg[s][k] = clock64(); } while (0)
 #else
 #define PROF_MARK(i) do { } while (0)
+#define DBG_MARK(s, k) do { } while (0)
 #endif
 
 // Row application a[j] -= tt * row[j] for j in (K, 32), `row` being a broadcast row of 32 doubles in
@@ -151,7 +205,7 @@ struct RowBatch {
 template <int K>
 struct DiagSweep {
   static __device__ __forceinline__ void run(double (&a)[SB], double* Bs, double* rd, double& dj, int& badcol, int lane,
-                                             double d) {
+                                             double d, int nconsumers) {
     __syncwarp();
     RowBatch<K> rb;
     rb.load(Bs + K * SB);
@@ -171,142 +225,216 @@ struct DiagSweep {
     }
     if (lane == K) { dj = d; rd[K] = fma(r0, pp, r0); }
     rb.apply_rest(a, tt);
-    DiagSweep<K + 1>::run(a, Bs, rd, dj, badcol, lane, dn);
+    if ((K & 7) == 7 && nconsumers > 0)           // columns K-7 .. K are published: release the warps below
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + (K >> 3)), "r"((nconsumers + 1) * 32) : "memory");
+    DiagSweep<K + 1>::run(a, Bs, rd, dj, badcol, lane, dn, nconsumers);
   }
 };
 template <>
 struct DiagSweep<SB> {
-  static __device__ __forceinline__ void run(double (&)[SB], double*, double*, double&, int&, int, double) {}
+  static __device__ __forceinline__ void run(double (&)[SB], double*, double*, double&, int&, int, double, int) {}
 };
+// Rows below the diagonal block: apply the published columns, eight at a time as the diagonal warp
+// releases them (named barriers 2..5).
 template <int K>
 struct BelowSweep {
-  static __device__ __forceinline__ void run(double (&a)[SB], const double* Bs, const double* rd) {
+  static __device__ __forceinline__ void run(double (&a)[SB], const double* Bs, const double* rd, int nthreads) {
+    if ((K & 7) == 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + (K >> 3)), "r"(nthreads) : "memory");
     RowBatch<K> rb;
     rb.load(Bs + K * SB);
     rb.apply(a, a[K] * rd[K]);
-    BelowSweep<K + 1>::run(a, Bs, rd);
+    BelowSweep<K + 1>::run(a, Bs, rd, nthreads);
   }
 };
 template <>
 struct BelowSweep<SB> {
-  static __device__ __forceinline__ void run(double (&)[SB], const double*, const double*) {}
+  static __device__ __forceinline__ void run(double (&)[SB], const double*, const double*, int) {}
 };
 
+// Rank-32 update of the trailing matrix by the sub-panel at columns c0 .. c0+31, lower 16x16 blocks
+// blk = first, first + stride, ..., on DMMA tiles.
+// PANEL = true:  the blocks (bi >= 2, bj < 2), i.e. the columns of the next sub-panel below its diagonal block;
+// PANEL = false: the blocks (bi >= bj >= 2), the trailing matrix behind the next sub-panel.
+template <bool PANEL>
+__device__ __forceinline__ void rank32_update(double* Lc, int c0, int first, int stride, int g, int t4) {
+  const int base = c0 + SB;
+  const int nb16 = (NB - base) / 16 - 2;         // block rows / columns behind the 32x32 block (s, s)
+  const int nblk = PANEL ? 2 * nb16 : nb16 * (nb16 + 1) / 2;
+  for (int blk = first; blk < nblk; blk += stride) {
+    int bi, bj;
+    if (PANEL) {
+      bi = 2 + (blk >> 1); bj = blk & 1;
+    } else {
+      bi = 0; bj = blk;
+      while (bj > bi) { bj -= bi + 1; ++bi; }
+      bi += 2; bj += 2;
+    }
+    const int i0 = base + 16 * bi, jj0 = base + 16 * bj;
+    double acc[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+#pragma unroll
+    for (int kq = 0; kq < SB / 4; ++kq) {
+      const double* colp = Lc + (c0 + 4 * kq + t4) * LD;
+      const double a0 = colp[i0 + g], a1 = colp[i0 + 8 + g];
+      const double b0 = colp[jj0 + g], b1 = colp[jj0 + 8 + g];
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+    // read-modify-write of the C block: all loads first (the compiler cannot reorder them past the stores itself)
+    double cv[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int row = i0 + 8 * x + g, col = jj0 + 8 * y + 2 * t4;
+        cv[x][y][0] = Lc[col * LD + row];
+        cv[x][y][1] = Lc[(col + 1) * LD + row];
+      }
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int row = i0 + 8 * x + g, col = jj0 + 8 * y + 2 * t4;
+        if (row >= col) Lc[col * LD + row] = cv[x][y][0] - acc[x][y][0];
+        if (row >= col + 1) Lc[(col + 1) * LD + row] = cv[x][y][1] - acc[x][y][1];
+      }
+  }
+}
 
 __global__ void __launch_bounds__(PT, 1)
 potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W, int* info) {
   extern __shared__ __align__(16) double Lc[];   // Lc[c * LD + r]
   double* dinv = Lc + NB * LD;                   // [NB]      1 / L_kk
-  double* Bs = dinv + NB;                        // [SB][SB]  unscaled diagonal block of the sub-panel, Bs[k][j] = S(c0+j, c0+k)
-  double* rd = Bs + SB * SB;                     // [SB]      1 / d_k   (pivot reciprocals)
-  double* rsq = rd + SB;                         // [SB]      1 / sqrt(d_k)
-  double* T = rsq + SB;                          // [3][SB][TLD] block temporaries of the inverse
+  double* Bs0 = dinv + NB;                       // 2 x { [SB][SB] unscaled diagonal block of the sub-panel, Bs[k][j] = S(c0+j, c0+k);
+                                                 //       [SB] 1 / d_k (pivot reciprocals); [SB] 1 / sqrt(d_k) }, by parity of the sub-panel
+  double* T = Bs0 + 2 * (SB * SB + 2 * SB);      // [3][SB][TLD] block temporaries of the inverse
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;        // DMMA fragment coordinates
 #ifdef CIP_POTRF_PROF
   long long prof_t[16];
+  __shared__ long long dbg[4][8];
 #endif
   PROF_MARK(0);
   {
-    const int r = tid & 127;
-    for (int q = tid >> 7; q < 32; q += PT / 128) {
-      if (4 * q > r) continue;                   // strictly-upper quads are never read
-      const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + q) * ld + j0 + r) * 4);
-      const double2 v0 = p[0], v1 = p[1];
-      Lc[(4 * q + 0) * LD + r] = v0.x;
-      Lc[(4 * q + 1) * LD + r] = v0.y;
-      Lc[(4 * q + 2) * LD + r] = v1.x;
-      Lc[(4 * q + 3) * LD + r] = v1.y;
+    // all 32-byte loads of a thread in flight before the first store (sixteen quads, two batches of eight)
+    const int r = tid & 127, qh = tid >> 7;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double2 v0[8], v1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = qh + 2 * (8 * half + u);
+        if (4 * q <= r) {                        // strictly-upper quads are never read
+          const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + q) * ld + j0 + r) * 4);
+          v0[u] = p[0];
+          v1[u] = p[1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = qh + 2 * (8 * half + u);
+        if (4 * q <= r) {
+          Lc[(4 * q + 0) * LD + r] = v0[u].x;
+          Lc[(4 * q + 1) * LD + r] = v0[u].y;
+          Lc[(4 * q + 2) * LD + r] = v1[u].x;
+          Lc[(4 * q + 3) * LD + r] = v1[u].y;
+        }
+      }
     }
   }
   __syncthreads();
   PROF_MARK(1);
 
+  // Sub-panel s = columns c0 .. c0+31.  Iteration s first applies the rank-32 update of sub-panel s-1 with
+  // look-ahead, then sweeps:
+  //   warp s           waits until block (s, s) has been updated (barrier 7), eliminates it, publishing its columns
+  //                    eight at a time (bar.arrive 2..5) and the scaling (6); stores its rows after the iteration's
+  //                    closing barrier, nobody needs them before the inverse
+  //   warp s+4         idle: it shares the scheduler (and the FP64 pipe) with warp s
+  //   the other six    update block (s, s) first (bar.arrive 7; not warp s-1, which is still storing), then the
+  //                    columns of this sub-panel below it (barrier 1); then warps s+1 .. 3 apply the published
+  //                    columns to their rows while the others update the trailing matrix behind the sub-panel
   for (int s = 0; s < NB / SB; ++s) {
     const int c0 = s * SB;
-    // ---- sub-panel sweep: thread = row i (warps 0..3), a[j] = S(i, c0 + j)
-    if (w < NB / SB && w >= s) {
+    const int nbelow = NB / SB - 1 - s;
+    double* Bs = Bs0 + (s & 1) * (SB * SB + 2 * SB);
+    double* rd = Bs + SB * SB;
+    double* rsq = rd + SB;
+    if (w == s) {
+      DBG_MARK(s, 0);
+      if (s > 0) asm volatile("bar.sync 7, 192;" ::: "memory");
       const int i = tid;
       double a[SB];
 #pragma unroll
       for (int j = 0; j < SB; ++j) {
-        const double v = Lc[(c0 + j) * LD + i];     // unconditional load + select: no divergence in the diagonal warp
-        a[j] = (c0 + j <= i) ? v : 0.0;
+        const double v = Lc[(c0 + j) * LD + i];        // unconditional load + select: no divergence
+        a[j] = (j <= lane) ? v : 0.0;
       }
-#ifdef CIP_POTRF_PROF
-      long long q0 = clock64(), q1 = 0, q2 = 0, q3 = 0;
-#endif
-      if (w == s) {
-        // the diagonal 32x32 block, warp-synchronous
-        double dj = 1.0;
-        int badcol = 0;
-        Bs[lane] = a[0];
-        DiagSweep<0>::run(a, Bs, rd, dj, badcol, lane, __shfl_sync(0xffffffffu, a[0], 0));
-        if (badcol && lane == 0) atomicCAS(info, 0, j0 + c0 + badcol);
-#ifdef CIP_POTRF_PROF
-        q1 = clock64();
-#endif
-        const double rs = 1.0 / sqrt(dj);
-        rsq[lane] = rs;
-        dinv[c0 + lane] = rs;
-        a[0] = (lane == 0) ? dj : a[0];          // diagonal entry: d_j / sqrt(d_j); set per lane below
+      double dj = 1.0;
+      int badcol = 0;
+      DBG_MARK(s, 1);
+      Bs[lane] = a[0];
+      DiagSweep<0>::run(a, Bs, rd, dj, badcol, lane, __shfl_sync(0xffffffffu, a[0], 0), nbelow);
+      if (badcol && lane == 0) atomicCAS(info, 0, j0 + c0 + badcol);
+      const double rsj = fast_rsqrt(dj);
+      rsq[lane] = rsj;
+      dinv[c0 + lane] = rsj;
+      if (nbelow > 0) asm volatile("bar.arrive 6, %0;" ::"r"((nbelow + 1) * 32) : "memory");
+      DBG_MARK(s, 2);
+      __syncthreads();                                 // closes iteration s
+      // L(i, c0 + j) = a[j] / sqrt(d_j), diagonal d_j / sqrt(d_j).  Entries right of the diagonal land in the
+      // free triangle (garbage, overwritten by the inverse later): no predicate, no divergence
+      double rq[SB];
 #pragma unroll
-        for (int j = 1; j < SB; ++j) a[j] = (lane == j) ? dj : a[j];
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"((NB / SB - s) * 32) : "memory");
-#ifdef CIP_POTRF_PROF
-      q2 = clock64();
-#endif
-      if (w > s) {
-        // rows below the diagonal block: apply the 32 published columns (no further synchronisation)
-        BelowSweep<0>::run(a, Bs, rd);
-      }
-#ifdef CIP_POTRF_PROF
-      q3 = clock64();
-      if (lane == 0 && j0 == 256 && CIP_POTRF_PROF > 1) printf("  s=%d w=%d: load+diag %lld | sqrt+bar %lld | below %lld (t0 %lld)\n", s, w, q1 ? q1 - q0 : 0, q2 - (q1 ? q1 : q0), q3 - q2, q0 - prof_t[0]);
-#endif
-      // L(i, c0 + j) = a[j] / sqrt(d_j)
+      for (int j = 0; j < SB; ++j) rq[j] = rsq[j];
 #pragma unroll
-      for (int j = 0; j < SB; ++j)
-        if (c0 + j <= i) Lc[(c0 + j) * LD + i] = a[j] * rsq[j];
-    }
-    __syncthreads();
-    PROF_MARK(2 + 2 * s);
-    // ---- rank-32 update of the trailing columns, lower 16x16 blocks, DMMA
-    const int base = c0 + SB;
-    const int nb16 = (NB - base) / 16;
-    const int nblk = nb16 * (nb16 + 1) / 2;
-    for (int blk = w; blk < nblk; blk += PW) {
-      int bi = 0, bj = blk;
-      while (bj > bi) { bj -= bi + 1; ++bi; }
-      const int i0 = base + 16 * bi, jj0 = base + 16 * bj;
-      double acc[2][2][2];
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-#pragma unroll
-      for (int kq = 0; kq < SB / 4; ++kq) {
-        const double* colp = Lc + (c0 + 4 * kq + t4) * LD;
-        const double a0 = colp[i0 + g], a1 = colp[i0 + 8 + g];
-        const double b0 = colp[jj0 + g], b1 = colp[jj0 + 8 + g];
-        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
-        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
-        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
-        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
-      }
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 2; ++y) {
-          const int row = i0 + 8 * x + g, col = jj0 + 8 * y + 2 * t4;
-          if (row >= col) Lc[col * LD + row] -= acc[x][y][0];
-          if (row >= col + 1) Lc[(col + 1) * LD + row] -= acc[x][y][1];
+      for (int j = 0; j < SB; ++j) Lc[(c0 + j) * LD + i] = ((j == lane) ? dj : a[j]) * rq[j];
+      DBG_MARK(s, 3);
+    } else {
+      if (s > 0 && w != s + 4) {
+        if (w != s - 1) {                              // warp s-1 is still storing its rows of sub-panel s-1
+          const int idx5 = w - (w > s - 1) - (w > s) - (w > s + 4);     // 0 .. 4
+          own_block_update(Lc, c0 - SB, idx5, PW - 3, g, t4);
+          asm volatile("bar.arrive 7, 192;" ::: "memory");
         }
+        const int idx6 = w - (w > s) - (w > s + 4);    // 0 .. 5
+        rank32_update<true>(Lc, c0 - SB, idx6, PW - 2, g, t4);      // the columns of this sub-panel
+      }
+      if (w == 7) DBG_MARK(s, 4);
+      asm volatile("bar.sync 1, %0;" ::"r"((PW - 1) * 32) : "memory");
+      if (w == 3) DBG_MARK(s, 5);
+      if (s > 0 && w != s + 4 && !(w > s && w < NB / SB)) {
+        // the trailing matrix behind this sub-panel, by the warps that have no rows to sweep
+        const int nfree = PW - 2 - nbelow;
+        const int idxf = (w < s) ? w : w - (NB / SB) - (w > s + 4) + s;   // warps 0 .. s-1, then 4 .. 7 without s + 4
+        rank32_update<false>(Lc, c0 - SB, idxf, nfree, g, t4);
+      }
+      if (w > s && w < NB / SB) {
+        const int i = tid;
+        double a[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) a[j] = Lc[(c0 + j) * LD + i];
+        BelowSweep<0>::run(a, Bs, rd, (nbelow + 1) * 32);
+        asm volatile("bar.sync 6, %0;" ::"r"((nbelow + 1) * 32) : "memory");
+        double rq[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) rq[j] = rsq[j];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) Lc[(c0 + j) * LD + i] = a[j] * rq[j];
+        if (w == 3) DBG_MARK(s, 6);
+      }
+      __syncthreads();                                 // closes iteration s
     }
-    __syncthreads();
+    if (w == 0) DBG_MARK(s, 7);
+    PROF_MARK(2 + 2 * s);
     PROF_MARK(3 + 2 * s);
   }
+  __syncthreads();                                     // the last diagonal warp has stored its rows
 
   // ---- write L back: the quads up to the diagonal (zeros right of it inside the last one; the quads
   //      beyond are never read by anyone).  Only reads the lower triangle, so it needs no barrier
@@ -376,6 +504,10 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   __syncthreads();
   PROF_MARK(15);
   if (tid == 0 && j0 == 256) {
+    for (int s = 0; s < 4; ++s)
+      printf("  s=%d: diag start %lld | own update %lld | load %lld... D %lld | store %lld || w7 update done %lld | w3 after bar1 %lld | w3 below done %lld | iteration end %lld\n", s,
+             dbg[s][0] - prof_t[0], 0LL, dbg[s][1] - dbg[s][0], dbg[s][2] - dbg[s][1], dbg[s][3] - dbg[s][2], dbg[s][4] - dbg[s][0],
+             dbg[s][5] - dbg[s][0], dbg[s][6] - dbg[s][0], dbg[s][7] - dbg[s][0]);
     printf("potrf prof (cycles): load %lld |", prof_t[1] - prof_t[0]);
     for (int i = 0; i < 4; ++i) printf(" sweep%d %lld upd%d %lld |", i, prof_t[2 + 2 * i] - prof_t[1 + 2 * i], i, prof_t[3 + 2 * i] - prof_t[2 + 2 * i]);
     printf(" writeL %lld | invdiag %lld | inv1 %lld inv2 %lld inv3 %lld | writeW %lld | total %lld\n", prof_t[10] - prof_t[9],

@@ -359,6 +359,7 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
   //   the other six    update block (s, s) first (bar.arrive 7; not warp s-1, which is still storing), then the
   //                    columns of this sub-panel below it (barrier 1); then warps s+1 .. 3 apply the published
   //                    columns to their rows while the others update the trailing matrix behind the sub-panel
+#pragma unroll 1
   for (int s = 0; s < NB / SB; ++s) {
     const int c0 = s * SB;
     const int nbelow = NB / SB - 1 - s;
@@ -367,7 +368,7 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
     double* rsq = rd + SB;
     if (w == s) {
       DBG_MARK(s, 0);
-      if (s > 0) asm volatile("bar.sync 7, 192;" ::: "memory");
+      asm volatile("bar.sync 7, 192;" ::: "memory");   // block (s, s) is up to date
       const int i = tid;
       double a[SB];
 #pragma unroll
@@ -396,12 +397,14 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
       for (int j = 0; j < SB; ++j) Lc[(c0 + j) * LD + i] = ((j == lane) ? dj : a[j]) * rq[j];
       DBG_MARK(s, 3);
     } else {
+      // barrier 7 is unconditional (five arrivals + the diagonal warp, also when there is nothing to update at
+      // s = 0): a conditional one makes the compiler peel the first iteration and duplicate the unrolled sweeps
+      if (w != s + 4 && w != (s + NB / SB - 1) % (NB / SB)) {   // not warp s-1: it is still storing its rows of sub-panel s-1
+        const int idx5 = w - (w > s - 1) - (w > s) - (w > s + 4);     // 0 .. 4
+        if (s > 0) own_block_update(Lc, c0 - SB, idx5, PW - 3, g, t4);
+        asm volatile("bar.arrive 7, 192;" ::: "memory");
+      }
       if (s > 0 && w != s + 4) {
-        if (w != s - 1) {                              // warp s-1 is still storing its rows of sub-panel s-1
-          const int idx5 = w - (w > s - 1) - (w > s) - (w > s + 4);     // 0 .. 4
-          own_block_update(Lc, c0 - SB, idx5, PW - 3, g, t4);
-          asm volatile("bar.arrive 7, 192;" ::: "memory");
-        }
         const int idx6 = w - (w > s) - (w > s + 4);    // 0 .. 5
         rank32_update<true>(Lc, c0 - SB, idx6, PW - 2, g, t4);      // the columns of this sub-panel
       }

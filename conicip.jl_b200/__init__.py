@@ -15,6 +15,7 @@ from .blocks import Block, DeviceBlock, Diagonal, SymWoodbury, VecCongurance  # 
 from .engine import Engine, measure_fp64_peaks, nccl_unique_id  # noqa: F401
 from .kktsolver import kktsolver_b200, make_kktsolver  # noqa: F401
 from .driver import Solution, conicIP, conicIP_native  # noqa: F401
+from .preprocess import imcols, preprocess_conicIP  # noqa: F401
 from . import problems, dist  # noqa: F401
 
 __version__ = "0.1.0"

@@ -93,6 +93,8 @@ SIGNATURES = {
     "cip_stream": (C.c_void_p, [C.c_void_p]),
     "cip_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cip_measure_fp64_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cip_imcols": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
+                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 

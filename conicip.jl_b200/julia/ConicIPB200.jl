@@ -194,6 +194,19 @@ function conicIP_b200(Q, c::AbstractVector, A, b::AbstractVector, cone_dims,
     return ConicIP.Solution(y, w, v, STATUS[r.status + 1], r.Iter, r.Mu, r.prFeas, r.duFeas, r.muFeas, r.pobj, r.dobj)
 end
 
+# ---- preprocessor (SURVEY 8f rank 4): drop-in for ConicIP.imcols (src/preprocessor.jl:10-28) on the device.
+# Returns (R, consistent) with 1-based sorted row indices, R empty when the system is inconsistent.
+function imcols_b200(A, b, ϵ = 1e-8; device = -1)
+    Ad = Matrix{Float64}(A); p, n = size(Ad)
+    keep = zeros(Cint, max(p, 1)); nkeep = Ref{Cint}(0); cons = Ref{Cint}(1)
+    check(ccall((:cip_imcols, LIB), Cint,
+                (Cint, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cdouble}, Cdouble, Ptr{Cint}, Ref{Cint}, Ref{Cint}),
+                device, Ad, max(p, 1), p, n, Vector{Float64}(b), ϵ, keep, nkeep, cons))
+    cons[] == 0 && return (Int[], false)
+    return (findall(!iszero, keep[1:p]), true)
+end
+# `preprocess_conicIP` itself needs no change beyond calling imcols_b200 at src/preprocessor.jl:58-59.
+
 # ---- MOI: `ConicIP.Optimizer` has no kktsolver field (src/MOI_wrapper.jl:19-31) and optimize!
 # forwards only verbose/optTol/maxIters (:278-282).  The one-field extension a maintainer adds:
 #

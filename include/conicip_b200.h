@@ -213,6 +213,18 @@ int cip_set_stream(cip_handle h, void* stream);
 /* FP64 pipe ceilings measured on this device: DMMA.8x8x4 and DFMA register-only loops */
 int cip_measure_fp64_peaks(int device, double* dmma_tflops, double* dfma_tflops);
 
+/* ---------------------------------------------------------------- preprocessor
+ * Replaces imcols(A, b, eps) -- src/preprocessor.jl:10-28, called twice by preprocess_conicIP (:58-59) on
+ * (G, d) and on ([Q A' G[IP,:]'], c): a maximal set of linearly independent rows of the p x n matrix A
+ * (rows whose pivot |R_kk| / ||A||_F exceeds eps in a row-pivoted QR of A') and the consistency of
+ * A x = b on the dropped rows (norm(A (A[R,:] \ b[R]) - b, Inf) / ||A||_F < eps).
+ *   A     column-major, leading dimension lda >= p; host or device pointer.  b likewise, length p.
+ *   keep  [p] out: 1 for the rows of the independent set, 0 for redundant ones;  *nkeep = their number
+ *   *consistent  out: 1 / 0.   (The reference returns an empty set when inconsistent; the caller decides.)
+ * No handle: it runs before cip_create on the device given (-1 = current).  Returns 0, or <0 on error. */
+int cip_imcols(int device, const double* A, int lda, int p, int n, const double* b, double eps, int* keep,
+               int* nkeep, int* consistent);
+
 #ifdef __cplusplus
 }
 #endif

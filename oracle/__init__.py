@@ -26,3 +26,4 @@ from .cones import (  # noqa: F401
 )
 from .kkt import kktsolver_qr, kktsolver_2x2, pivot, kktsolver_chol  # noqa: F401
 from .conicip import conicIP, Solution  # noqa: F401
+from .preprocess import imcols, preprocess_conicIP  # noqa: F401

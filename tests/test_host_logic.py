@@ -149,3 +149,24 @@ def test_bench_reference_arm_schema():
         assert k in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_imcols_paths_that_need_no_device():
+    """cip_imcols answers the empty matrix like the reference (src/preprocessor.jl:15: `([], true)`) and rejects
+    bad arguments before touching CUDA, so both are checkable on the CPU box."""
+    import ctypes as C
+
+    import conicip_b200 as cb
+    from conicip_b200._lib import lib, last_error
+
+    R, ok = cb.imcols(np.zeros((0, 7)), np.zeros(0))
+    assert ok and len(R) == 0
+    R, ok = cb.imcols(np.zeros((3, 0)), np.zeros(3))
+    assert ok and len(R) == 0
+    keep = (C.c_int * 4)()
+    nk, cons = C.c_int(0), C.c_int(0)
+    A = np.zeros((4, 2))
+    rc = lib().cip_imcols(-1, A.ctypes.data, 2, 4, 2, A.ctypes.data, 1e-8, keep, C.byref(nk), C.byref(cons))   # lda < p
+    assert rc == -2 and "cip_imcols" in last_error()
+    with pytest.raises(ValueError):
+        cb.imcols(np.zeros((3, 2)), np.zeros(5))

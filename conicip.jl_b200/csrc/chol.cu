@@ -14,15 +14,6 @@ namespace cip {
 namespace {
 constexpr int NB = 128;
 
-__device__ __forceinline__ double fast_rcp(double d) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));   // ~20 bits; two Newton steps -> full double
-  double e = fma(-d, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  return fma(x, e, x);
-}
-
 // 1 / sqrt(d), branch-free (the IEEE sqrt and division sequences carry slow-path branches that cut the
 // instruction stream of the sweep into pieces): 20-bit seed, one third-order step, |e|^3 < 2^-60.
 __device__ __forceinline__ double fast_rsqrt(double d) {

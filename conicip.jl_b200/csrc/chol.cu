@@ -45,6 +45,7 @@ constexpr int LD = 132;          // column stride of the shared block
 constexpr int TLD = 36;          // row stride of the 32x32 T blocks of the inverse
 constexpr int PT = 256;          // threads of potrf_diag_kernel: 8 warps, so that a thread may hold ~250 registers (row + load batch)
 constexpr int PW = PT / 32;
+static_assert(PW == 8 && NB / SB == 4, "the named-barrier thread counts (192, 224) and the warp roles of potrf_diag_kernel assume 8 warps and 4 sub-panels");
 constexpr int POTRF_SMEM = (NB * LD + NB + 2 * (SB * SB + 2 * SB) + 3 * SB * TLD) * (int)sizeof(double);
 
 // X(rr, cc) of the (partially built) inverse: strict lower part from the free triangle, diagonal from dinv

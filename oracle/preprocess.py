@@ -23,12 +23,18 @@ def imcols(A, b, eps=1e-8):
     nA = np.linalg.norm(A)                            # :13  (Frobenius)
     A = A / nA
     b = b / nA
-    _, Rm, piv = sla.qr(A.T, mode="economic", pivoting=True)       # :17-21
+    Qm, Rm, piv = sla.qr(A.T, mode="economic", pivoting=True)      # :17-21
     diag = np.abs(np.diag(Rm))
-    R = np.sort(piv[:len(diag)][diag > eps])          # :22
+    r = int(np.count_nonzero(diag > eps))             # dgeqp3's diagonal is non-increasing in magnitude
+    sel = piv[:r]
+    R = np.sort(sel)                                  # :22
     if len(R) == 0:                                   # :24
         return np.zeros(0, dtype=np.int64), True
-    x = np.linalg.lstsq(A[R, :], b[R], rcond=None)[0]              # A[R,:] \ b[R]  (minimum norm), :26
+    # A[R,:] \ b[R] (:26): Julia solves the wide system through a QR factorisation (minimum-norm solution); the
+    # same here from the factorisation at hand, A[sel,:]' = Qm[:, :r] Rm[:r, :r].  (An SVD-based lstsq leaves a
+    # ten times larger residual, enough to flip the absolute 1e-8 test on badly scaled data: Miles problem 3.)
+    y = sla.solve_triangular(Rm[:r, :r], b[sel], trans="T", lower=False)
+    x = Qm[:, :r] @ y
     ok = bool(np.linalg.norm(A @ x - b, np.inf) < eps)
     return (R, True) if ok else (np.zeros(0, dtype=np.int64), False)
 

@@ -1,4 +1,4 @@
-"""Loader for tests/golden/miles_problems.json and a restatement of the reference's test-side conversion
+"""Loader for tests/golden/miles_problems.npz and a restatement of the reference's test-side conversion
 `mpb_to_conicip` (test/testdata.jl:15-102): MathProgBase form  min c'x  s.t.  b - Ax in K_con, x in K_var
 ->  solver form  min 1/2 y'Qy - c'y  s.t.  Ay - b in K, Gy = d."""
 import json
@@ -10,8 +10,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def load():
-    with open(os.path.join(_HERE, "miles_problems.json")) as f:
-        return {p["name"]: p for p in json.load(f)["problems"]}
+    z = np.load(os.path.join(_HERE, "miles_problems.npz"))
+    out = {}
+    for p in json.loads(str(z["meta"]))["problems"]:
+        for key in ("c", "b", "I", "J", "V"):
+            p[key] = z[f"{p['name']}.{key}"]
+        out[p["name"]] = p
+    return out
 
 
 def mpb_arrays(p):

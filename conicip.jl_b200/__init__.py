@@ -12,7 +12,7 @@ Public surface (mirrors the reference's names for this path):
 from ._lib import (BLK_DIAG, BLK_VECCONG, BLK_WOODBURY, CONE_Q, CONE_R, CONE_S,  # noqa: F401
                    OP_F, OP_FINV, OP_FINVT, OP_FT, CipError, LIB_PATH, SIGNATURES, lib)
 from .blocks import Block, DeviceBlock, Diagonal, SymWoodbury, VecCongurance  # noqa: F401
-from .engine import Engine, measure_fp64_peaks, nccl_unique_id  # noqa: F401
+from .engine import Engine, measure_fp64_peaks, nccl_unique_id, shard_plan  # noqa: F401
 from .kktsolver import kktsolver_b200, make_kktsolver  # noqa: F401
 from .driver import Solution, conicIP, conicIP_native  # noqa: F401
 from .preprocess import imcols, preprocess_conicIP  # noqa: F401

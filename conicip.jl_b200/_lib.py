@@ -18,7 +18,8 @@ CONE_CODE = {"R": CONE_R, "Q": CONE_Q, "S": CONE_S}
 
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("device", C.c_int), ("reg_delta", C.c_double),
-                ("reg_eps_G", C.c_double), ("q_kind", C.c_int), ("verbose", C.c_int), ("dist_chol", C.c_int), ("aug_rho", C.c_double)]
+                ("reg_eps_G", C.c_double), ("q_kind", C.c_int), ("verbose", C.c_int), ("dist_chol", C.c_int), ("aug_rho", C.c_double),
+                ("ngpus", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "cip_create_csc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Csc), C.POINTER(Csc), C.POINTER(Csc),
                                  C.c_int, _P, _P, C.POINTER(Options)]),
     "cip_destroy": (C.c_int, [C.c_void_p]),
+    "cip_shard_plan": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _P]),
     "cip_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "cip_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "cip_factor": (C.c_int, [C.c_void_p, _P, _P, _P, _P, _P]),

@@ -29,8 +29,16 @@ class SymWoodbury:
 
     def __init__(self, A_diag, B, D):
         self.A_diag = np.ascontiguousarray(A_diag, dtype=np.float64)
-        self.B = np.ascontiguousarray(B, dtype=np.float64).ravel()
-        self.D = float(D)
+        B = np.asarray(B, dtype=np.float64)
+        D = np.asarray(D, dtype=np.float64)
+        # WoodburyMatrices' general form (matrix B of rank > 1, matrix D: src/blockmatrices.jl:135-141,
+        # src/kktsolvers.jl:73-90) is never produced by conicIP (nestod_soc builds rank 1, src/ConicIP.jl:192)
+        # and the engine's flat format cannot carry it: reject it loudly instead of flattening it wrongly
+        if (B.ndim == 2 and B.shape[1] != 1) or B.size != self.A_diag.size or D.size != 1:
+            raise ValueError("SymWoodbury blocks of rank > 1 (matrix B / matrix D) are not supported by the "
+                             "B200 engine; only the rank-1 form diag(A) + B*D*B' that nestod_soc builds is")
+        self.B = np.ascontiguousarray(B).ravel()
+        self.D = float(D.ravel()[0])
 
     @property
     def size(self):
@@ -64,6 +72,23 @@ class Block:
     @property
     def size(self):
         return sum(b.size for b in self.Blocks)
+
+    @classmethod
+    def from_flat(cls, cone_dims, kind, fa, fb, fD, Rs=None):
+        """Inverse of `flatten`: rebuild the host Block from the arrays `cip_get_scaling` returns."""
+        blocks, off, si = [], 0, 0
+        for i, (t, k) in enumerate(cone_dims):
+            k = int(k)
+            if kind[i] == BLK_DIAG:
+                blocks.append(Diagonal(fa[off:off + k]))
+            elif kind[i] == BLK_WOODBURY:
+                blocks.append(SymWoodbury(fa[off:off + k], fb[off:off + k], fD[i]))
+            else:
+                blocks.append(VecCongurance(Rs[si]))
+            if t == "S":
+                si += 1
+            off += k
+        return cls(blocks)
 
     def flatten(self):
         """-> (kind int32[nc], fa f64[m], fb f64[m], fD f64[nc], fR f64[sum k^2] or None)."""

@@ -619,7 +619,7 @@ trsv_bwd_kernel(const double* __restrict__ H, int ld, const double* __restrict__
   }
 }
 
-bool g_potrf_attr = false;
+std::atomic<unsigned long long> g_potrf_attr{0};
 }  // namespace
 
 int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info) {
@@ -655,10 +655,7 @@ void chol_free_plan(CholPlan* p) {
 int chol_factor(const CholPlan& p, cudaStream_t s) {
   constexpr int OUTER = 4;
   const int smem = POTRF_SMEM;
-  if (!g_potrf_attr) {
-    CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    g_potrf_attr = true;
-  }
+  CIP_TRY(ensure_dyn_smem((const void*)potrf_diag_kernel, smem, &g_potrf_attr));
   cudaStream_t sc = p.sc;
   const int np = p.npanels;
   CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));
@@ -764,10 +761,7 @@ int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
   const NcclApi* api = nccl_api();
   if (!api) return -1;
   const int smem = POTRF_SMEM;
-  if (!g_potrf_attr) {
-    CIP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    g_potrf_attr = true;
-  }
+  CIP_TRY(ensure_dyn_smem((const void*)potrf_diag_kernel, smem, &g_potrf_attr));
   cudaStream_t sc = p.sc;
   const int np = p.npanels, NO = (np + OUTER - 1) / OUTER, N = d.nranks, me = d.rank;
   CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));

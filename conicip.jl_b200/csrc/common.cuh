@@ -4,13 +4,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace cip {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
-extern long long g_launches;   // kernels launched by this library (cip_stats.kernel_launches)
+extern std::atomic<long long> g_launches;   // kernels launched by this library (cip_stats.kernel_launches)
+// Number of SMs of the current device (cached per device; grids are sized from it, never from a literal).
+int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: `done` is a per-kernel bit mask over device
+// ordinals, so a process that drives several GPUs (single-process multi-GPU handles) sets it once on each.
+int ensure_dyn_smem(const void* func, int bytes, std::atomic<unsigned long long>* done);
 
 #define CIP_CUDA(expr)                                                              \
   do {                                                                              \

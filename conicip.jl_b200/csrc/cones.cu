@@ -377,7 +377,8 @@ scale_panel_wood_kernel(ConeDesc c, Scaling Fi, const double* __restrict__ At4, 
 
 inline int nblocks(int n, int per) {
   int b = (n + per - 1) / per;
-  return b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b);
+  const int cap = sm_count() * 16;
+  return b < 1 ? 1 : (b > cap ? cap : b);
 }
 
 }  // namespace
@@ -464,8 +465,8 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
   else if (c.nr_rows > 0) maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
   CIP_CHECK_LAUNCH();
   if (c.nq > 0) {
-    if (c.max_q_dim > 1024) maxstep_q_kernel<256><<<std::min(c.nq, 148 * 8), 256, 0, st>>>(c, x, d, d_scale, key);
-    else maxstep_q_kernel<32><<<std::min((c.nq + 7) / 8, 148 * 8), 256, 0, st>>>(c, x, d, d_scale, key);
+    if (c.max_q_dim > 1024) maxstep_q_kernel<256><<<std::min(c.nq, sm_count() * 8), 256, 0, st>>>(c, x, d, d_scale, key);
+    else maxstep_q_kernel<32><<<std::min((c.nq + 7) / 8, sm_count() * 8), 256, 0, st>>>(c, x, d, d_scale, key);
     CIP_CHECK_LAUNCH();
   }
   CIP_TRY(sdp_maxstep(c, x, d, d_scale, key, st));

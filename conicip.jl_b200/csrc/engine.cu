@@ -21,7 +21,29 @@
 namespace cip {
 
 static thread_local char g_err[1024] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+int ensure_dyn_smem(const void* func, int bytes, std::atomic<unsigned long long>* done) {
+  int dev = 0;
+  CIP_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done->load(std::memory_order_acquire) & bit) return 0;
+  CIP_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done->fetch_or(bit, std::memory_order_release);
+  return 0;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -54,6 +76,16 @@ bool is_device_ptr(const void* p) {
   }
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
+// memory a kernel running on `device` may dereference: managed memory, or device memory of that very device
+// (a shard of a multi-GPU handle is handed pointers that live on another GPU: those go through a copy)
+bool kernel_readable(const void* p, int device) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeManaged || (at.type == cudaMemoryTypeDevice && at.device == device);
+}
 
 // stage an input vector (host or device) into an internal zero-padded device buffer
 int stage_in(cip_engine* h, double* dst, const double* src, size_t n) {
@@ -72,7 +104,7 @@ int stage_out(cip_engine* h, double* dst, const double* src, size_t n) {
   return 0;
 }
 int finish(cip_engine* h) {
-  if (h->need_sync) {
+  if (h->need_sync || h->always_sync) {
     CIP_CUDA(cudaStreamSynchronize(h->stream));
     h->need_sync = false;
   }
@@ -122,6 +154,12 @@ int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, cons
       any_v = true;
     } else if (hk[i] != CIP_BLK_DIAG && hk[i] != CIP_BLK_WOODBURY) {
       set_error("unknown scaling block kind %d for cone %d", hk[i], i);
+      return -1;
+    }
+    if (hk[i] == CIP_BLK_WOODBURY && h->h_type[i] != CIP_CONE_Q) {
+      // nestod_soc is the only producer of SymWoodbury blocks (src/ConicIP.jl:192,599); the panel scaling
+      // only walks the Q cones, so a Woodbury block elsewhere would make H inconsistent with cip_apply
+      set_error("SymWoodbury block on cone %d, which is not a Q cone", i);
       return -1;
     }
     any_w |= (hk[i] == CIP_BLK_WOODBURY);
@@ -264,6 +302,7 @@ int factor_H(cip_engine* h) {
 
 namespace cip {
 int engine_allreduce(cip_engine* h, double* buf, size_t count) { return allreduce(h, buf, count); }
+const char* last_error_string() { return g_err; }
 }  // namespace cip
 
 // =================================================================== C ABI
@@ -293,9 +332,19 @@ int upload_csc(cip_engine* h, double* dst, int ld, const cip_csc* M, int transpo
   CIP_CUDA(cudaMemcpyAsync(dcp, M->colptr, (ncols + 1) * 8, cudaMemcpyDefault, h->stream));
   CIP_CUDA(cudaMemcpyAsync(drv, M->rowval, nnz * 8, cudaMemcpyDefault, h->stream));
   CIP_CUDA(cudaMemcpyAsync(dnz, M->nzval, nnz * 8, cudaMemcpyDefault, h->stream));
-  int rc = scatter_csc_q4(dst, ld, (int)ncols, dcp, drv, dnz, M->index_base, transpose, h->stream);
+  int* dbad = nullptr;
+  CIP_CUDA(cudaMalloc(&dbad, sizeof(int)));
+  CIP_CUDA(cudaMemsetAsync(dbad, 0, sizeof(int), h->stream));
+  int rc = scatter_csc_q4(dst, ld, (int)ncols, dcp, drv, dnz, M->index_base, transpose, M->nrows, nnz, dbad, h->stream);
+  int bad = 0;
+  cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
-  cudaFree(dcp); cudaFree(drv); cudaFree(dnz);
+  cudaFree(dcp); cudaFree(drv); cudaFree(dnz); cudaFree(dbad);
+  if (rc == 0 && bad != 0) {
+    set_error("malformed CSC input: column %d holds a row index outside [0, %d) or an inverted column pointer",
+              bad - 1, M->nrows);
+    return -1;
+  }
   return rc;
 }
 
@@ -451,7 +500,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
     CIP_TRY(upload_csc(h, h->Qq4, h->n_pad, Qs, 0));
   } else if (h->opt.q_kind == 0) {
     if (!Q) { set_error("Q is null"); return -1; }
-    if (is_device_ptr(Q)) {
+    if (kernel_readable(Q, h->device)) {
       CIP_TRY(pack_rows_q4(h->Qq4, h->n_pad, Q, ldq, n, n, h->n_pad, h->n_pad, s));
     } else {
       // chunk columns through a staging buffer
@@ -461,7 +510,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
       for (int c0 = 0; c0 < n; c0 += chunk) {
         const int nc = std::min(chunk, n - c0);
         CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)n * 8, Q + (size_t)c0 * ldq, (size_t)ldq * 8, (size_t)n * 8, nc,
-                                   cudaMemcpyHostToDevice, s));
+                                   cudaMemcpyDefault, s));
         // columns c0.. -> k range; write quads (c0/4 ..)
         CIP_TRY(pack_rows_q4(h->Qq4 + (size_t)(c0 / 4) * h->n_pad * 4, h->n_pad, stg, n, n, nc, h->n_pad,
                              round_up(nc, 4), s));
@@ -485,7 +534,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
     if (!A && !As) { set_error("A is null"); return -1; }
     if (As) {
       CIP_TRY(upload_csc(h, h->At4, h->n_pad, As, 1));
-    } else if (is_device_ptr(A)) {
+    } else if (kernel_readable(A, h->device)) {
       CIP_TRY(pack_trans_q4(h->At4, h->n_pad, 0, A, lda, m, h->m_pad, n, s));
     } else {
       const int chunk = std::max(1, std::min(n, (int)((512u << 20) / ((size_t)m * 8))));
@@ -494,7 +543,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
       for (int c0 = 0; c0 < n; c0 += chunk) {
         const int nc = std::min(chunk, n - c0);
         CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)m * 8, A + (size_t)c0 * lda, (size_t)lda * 8, (size_t)m * 8, nc,
-                                   cudaMemcpyHostToDevice, s));
+                                   cudaMemcpyDefault, s));
         CIP_TRY(pack_trans_q4(h->At4, h->n_pad, c0, stg, m, m, h->m_pad, nc, s));
         CIP_CUDA(cudaStreamSynchronize(s));
       }
@@ -520,9 +569,9 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
       double* stg = nullptr;
       const double* gsrc = G;
       int gld = ldg;
-      if (!is_device_ptr(G)) {
+      if (!kernel_readable(G, h->device)) {
         CIP_CUDA(cudaMalloc(&stg, (size_t)p * n * 8));
-        CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)p * 8, G, (size_t)ldg * 8, (size_t)p * 8, n, cudaMemcpyHostToDevice, s));
+        CIP_CUDA(cudaMemcpy2DAsync(stg, (size_t)p * 8, G, (size_t)ldg * 8, (size_t)p * 8, n, cudaMemcpyDefault, s));
         gsrc = stg;
         gld = p;
       }
@@ -542,7 +591,7 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
   for (auto& v : h->nv) CIP_TRY(dev_alloc(h, &v, h->n_pad + 4));
   for (auto& v : h->mv) CIP_TRY(dev_alloc(h, &v, h->m_pad + 4));
   for (auto& v : h->pv) CIP_TRY(dev_alloc(h, &v, h->p_pad + 4));
-  h->partial_cap = 4 * 148 * 8 * 128 + 64 * std::max(n, std::max(p, 1));
+  h->partial_cap = 4 * sm_count() * 8 * 128 + 64 * std::max(n, std::max(p, 1));
   CIP_TRY(dev_alloc(h, &h->partial, h->partial_cap));
   CIP_TRY(dev_alloc(h, &h->scalar, 8));
   CIP_CUDA(cudaStreamSynchronize(s));
@@ -552,11 +601,34 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
 
 }  // namespace
 
+namespace cip {
+int engine_create_single(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                         const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs,
+                         int ncones, const int* cone_type, const int* cone_dim, const cip_options* opts) {
+  return create_impl(out, n, m, p, Q, ldq, A, lda, G, ldg, Qs, As, Gs, ncones, cone_type, cone_dim, opts);
+}
+}  // namespace cip
+
+namespace {
+// opts.ngpus > 1 (and the field is inside the caller's struct): single-process multi-GPU handle
+bool wants_multi(const cip_options* opts) {
+  return opts && (size_t)opts->struct_size >= offsetof(cip_options, ngpus) + sizeof(int) && opts->ngpus > 1;
+}
+}  // namespace
+
 extern "C" {
 
 int cip_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
                const double* G, int ldg, int ncones, const int* cone_type, const int* cone_dim,
                const cip_options* opts) {
+  if (wants_multi(opts)) {
+    if (!out || n <= 0 || m < 0 || p < 0 || ncones < 0 || (ncones > 0 && (!cone_type || !cone_dim))) {
+      set_error("cip_create: bad dimensions n=%d m=%d p=%d ncones=%d", n, m, p, ncones);
+      return -1;
+    }
+    return multi_create(out, n, m, p, Q, ldq, A, lda, G, ldg, nullptr, nullptr, nullptr, ncones, cone_type,
+                        cone_dim, opts);
+  }
   return create_impl(out, n, m, p, Q, ldq, A, lda, G, ldg, nullptr, nullptr, nullptr, ncones, cone_type, cone_dim,
                      opts);
 }
@@ -575,12 +647,21 @@ int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, c
   o.struct_size = sizeof(o);
   o.q_kind = 2;                         // Q comes from the CSC arrays (or is zero when Q == NULL)
   const int p = G ? G->nrows : 0;
+  if (wants_multi(&o)) {
+    if (!out || n <= 0 || ncones < 0 || (ncones > 0 && (!cone_type || !cone_dim))) {
+      set_error("cip_create_csc: bad arguments");
+      return -1;
+    }
+    return multi_create(out, n, A->nrows, p, nullptr, 0, nullptr, 0, nullptr, 0, Q, A, (p > 0) ? G : nullptr, ncones,
+                        cone_type, cone_dim, &o);
+  }
   return create_impl(out, n, A->nrows, p, nullptr, 0, nullptr, 0, nullptr, 0, Q, A, (p > 0) ? G : nullptr, ncones,
                      cone_type, cone_dim, &o);
 }
 
 int cip_destroy(cip_handle h) {
   if (!h) return 0;
+  if (h->multi) return multi_destroy(h);
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->stream);
   if (h->comm) {
@@ -618,6 +699,7 @@ int cip_nccl_unique_id(unsigned char id_out[128]) {
 
 int cip_comm_init(cip_handle h, int nranks, int rank, const unsigned char id[128]) {
   CIP_TRY(check(h));
+  if (h->multi) { set_error("cip_comm_init: a single-process multi-GPU handle (opts.ngpus) owns its communicators"); return -1; }
   if (nranks <= 1) return 0;
   const NcclApi* api = nccl_api();
   if (!api) return -1;
@@ -637,17 +719,20 @@ int cip_comm_init(cip_handle h, int nranks, int rank, const unsigned char id[128
 int cip_set_scaling(cip_handle h, const int* kind, const double* fa, const double* fb, const double* fD,
                     const double* fR) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_factor(h, kind, fa, fb, fD, fR, 0);
   return set_scaling_from_user(h, kind, fa, fb, fD, fR);
 }
 
 int cip_form_H(cip_handle h) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_simple(h, 0, nullptr, 0);
   CIP_TRY(form_H(h));
   return 0;
 }
 
 int cip_factor_H(cip_handle h) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_simple(h, 1, nullptr, 0);
   CIP_CUDA(cudaEventRecord(h->ev[3], h->stream));
   return factor_H(h);
 }
@@ -655,6 +740,7 @@ int cip_factor_H(cip_handle h) {
 int cip_factor(cip_handle h, const int* kind, const double* fa, const double* fb, const double* fD,
                const double* fR) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_factor(h, kind, fa, fb, fD, fR, 1);
   CIP_TRY(set_scaling_from_user(h, kind, fa, fb, fD, fR));
   CIP_TRY(form_H(h));
   return factor_H(h);
@@ -662,22 +748,40 @@ int cip_factor(cip_handle h, const int* kind, const double* fa, const double* fb
 
 int cip_nt_scaling(cip_handle h, const double* v, const double* s, double* lambda_out) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_nt_scaling(h, v, s, lambda_out, 0);
   CIP_TRY(stage_in(h, h->mv[7], v, h->m));
   CIP_TRY(stage_in(h, h->mv[8], s, h->m));
+  if (h->cd.ns > 0) CIP_CUDA(cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
   CIP_TRY(cone_nt_scaling(h->cd, h->mv[7], h->mv[8], h->F, h->Fi, h->mv[9], h->info + 2, h->stream));
   h->have_scaling = true;
   CIP_TRY(stage_out(h, lambda_out, h->mv[9], h->m));
+  if (h->cd.ns > 0) {
+    // an S-cone iterate that is not positive definite has no NT scaling (PosDefException in the reference,
+    // src/ConicIP.jl:201-202): report it as a numerical failure (> 0) instead of handing out garbage
+    int bad = 0;
+    CIP_CUDA(cudaMemcpyAsync(&bad, h->info + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CIP_CUDA(cudaStreamSynchronize(h->stream));
+    h->need_sync = false;
+    if (bad != 0) {
+      h->have_scaling = false;
+      set_error("nt_scaling: the iterate of S cone %d is not positive definite (PosDefException in the reference)",
+                bad - 1);
+      return bad;
+    }
+  }
   return finish(h);
 }
 
 int cip_factor_from_point(cip_handle h, const double* v, const double* s, double* lambda_out) {
-  CIP_TRY(cip_nt_scaling(h, v, s, lambda_out));
+  if (h && h->multi) return multi_nt_scaling(h, v, s, lambda_out, 1);
+  CIP_TRY(cip_nt_scaling(h, v, s, lambda_out));      // > 0 (S-cone iterate not PD) is returned as it is
   CIP_TRY(form_H(h));
   return factor_H(h);
 }
 
 int cip_get_scaling(cip_handle h, int* kind, double* fa, double* fb, double* fD, double* fR) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_get_scaling(h, kind, fa, fb, fD, fR);
   if (!h->have_scaling) { set_error("no scaling set"); return -1; }
   if (kind) {
     CIP_CUDA(cudaMemcpyAsync(kind, h->F.kind, sizeof(int) * h->ncones, cudaMemcpyDefault, h->stream));
@@ -692,6 +796,7 @@ int cip_get_scaling(cip_handle h, int* kind, double* fa, double* fb, double* fD,
 
 int cip_apply(cip_handle h, int op, const double* x, double* y) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_apply(h, op, x, y);
   if (!h->have_scaling) { set_error("no scaling set"); return -1; }
   CIP_TRY(stage_in(h, h->mv[7], x, h->m));
   if (op < CIP_OP_F || op > CIP_OP_FINV) { set_error("cip_apply: bad op %d", op); return -1; }
@@ -702,6 +807,7 @@ int cip_apply(cip_handle h, int op, const double* x, double* y) {
 
 int cip_maxstep(cip_handle h, const double* x, const double* d, double d_scale, double* alpha_out) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_maxstep(h, x, d, d_scale, alpha_out);
   CIP_TRY(stage_in(h, h->mv[7], x, h->m));
   if (d) CIP_TRY(stage_in(h, h->mv[8], d, h->m));
   CIP_TRY(cone_maxstep(h->cd, h->mv[7], d ? h->mv[8] : nullptr, d_scale, nullptr, 0, h->scalar, h->stream));
@@ -717,6 +823,7 @@ int cip_maxstep(cip_handle h, const double* x, const double* d, double d_scale, 
 
 int cip_cone_prod(cip_handle h, const double* x, const double* y, double* o) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_prod_div(h, x, y, o, 0);
   CIP_TRY(stage_in(h, h->mv[7], x, h->m));
   CIP_TRY(stage_in(h, h->mv[8], y, h->m));
   CIP_TRY(cone_prod(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
@@ -726,6 +833,7 @@ int cip_cone_prod(cip_handle h, const double* x, const double* y, double* o) {
 
 int cip_cone_div(cip_handle h, const double* x, const double* y, double* o) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_prod_div(h, x, y, o, 1);
   CIP_TRY(stage_in(h, h->mv[7], x, h->m));
   CIP_TRY(stage_in(h, h->mv[8], y, h->m));
   CIP_TRY(cone_div(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
@@ -736,6 +844,7 @@ int cip_cone_div(cip_handle h, const double* x, const double* y, double* o) {
 int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv, double* dy, double* dw,
               double* dv) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_solve(h, ry, rw, rv, dy, dw, dv);
   if (!h->have_factor) { set_error("cip_solve before cip_factor"); return -1; }
   cudaStream_t s = h->stream;
   CIP_CUDA(cudaEventRecord(h->ev[6], s));
@@ -787,6 +896,7 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
 
 int cip_mul_A(cip_handle h, int trans, const double* x, double* y) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_mul_A(h, trans, x, y);
   cudaStream_t s = h->stream;
   if (!trans) {
     CIP_TRY(stage_in(h, h->nv[6], x, h->n));
@@ -804,6 +914,7 @@ int cip_mul_A(cip_handle h, int trans, const double* x, double* y) {
 
 int cip_mul_G(cip_handle h, int trans, const double* x, double* y) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_mul_GQ(h, 0, trans, x, y);
   cudaStream_t s = h->stream;
   if (h->p == 0) {
     if (trans) {
@@ -826,6 +937,7 @@ int cip_mul_G(cip_handle h, int trans, const double* x, double* y) {
 
 int cip_mul_Q(cip_handle h, const double* x, double* y) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_mul_GQ(h, 1, 0, x, y);
   cudaStream_t s = h->stream;
   CIP_TRY(stage_in(h, h->nv[6], x, h->n));
   CIP_TRY(q4_mv_rows(h->nv[7], h->Qq4, h->n_pad, h->n, h->n, h->nv[6], h->partial, h->partial_cap, s));
@@ -835,6 +947,7 @@ int cip_mul_Q(cip_handle h, const double* x, double* y) {
 
 int cip_stats(cip_handle h, cip_stats_t* out) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_stats(h, out);
   float ms = 0;
   if (h->st.solves > 0 && cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->st.ms_solve = ms;
   else cudaGetLastError();
@@ -846,6 +959,7 @@ int cip_stats(cip_handle h, cip_stats_t* out) {
 
 int cip_get_H(cip_handle h, double* out, int ldo) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_simple(h, 3, out, ldo);
   double* tmp = nullptr;
   CIP_CUDA(cudaMalloc(&tmp, (size_t)h->n * h->n * 8));
   CIP_TRY(unpack_rows_q4(tmp, h->n, h->H4, h->n_pad, h->n, h->n, h->stream));
@@ -858,14 +972,19 @@ int cip_get_H(cip_handle h, double* out, int ldo) {
 
 int cip_sync(cip_handle h) {
   CIP_TRY(check(h));
+  if (h->multi) return multi_simple(h, 2, nullptr, 0);
   CIP_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
-void* cip_stream(cip_handle h) { return h ? (void*)h->stream : nullptr; }
+void* cip_stream(cip_handle h) { return (h && !h->multi) ? (void*)h->stream : nullptr; }
 
 int cip_set_stream(cip_handle h, void* stream) {
   CIP_TRY(check(h));
+  if (h->multi) {
+    set_error("cip_set_stream: a single-process multi-GPU handle runs one stream per device; calls return with all of them idle");
+    return -1;
+  }
   CIP_CUDA(cudaStreamSynchronize(h->stream));
   h->stream = reinterpret_cast<cudaStream_t>(stream);
   return 0;

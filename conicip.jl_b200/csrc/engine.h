@@ -10,7 +10,15 @@ constexpr int NV = 8;   // n-length work vectors
 constexpr int MV = 10;  // m-length work vectors
 constexpr int PV = 6;   // p-length work vectors
 
+namespace cip { struct Multi; }
+
 struct cip_engine {
+  // single-process multi-GPU: a handle created with opts.ngpus > 1 is only a front for `multi` (one shard
+  // engine per device, each driven by its own host thread); a shard engine points back through `parent`
+  cip::Multi* multi = nullptr;
+  cip::Multi* parent = nullptr;
+  int shard_index = 0;
+  bool always_sync = false;   // shard engines: every call returns with its stream idle (outputs may live on another device)
   int n = 0, m = 0, p = 0, n_pad = 0, m_pad = 0, p_pad = 0, ncones = 0;
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -54,4 +62,31 @@ struct cip_engine {
 namespace cip {
 // sum-all-reduce `count` doubles in place across the row shards (no-op for a single GPU)
 int engine_allreduce(cip_engine* h, double* buf, size_t count);
+// cip_create / cip_create_csc for one device (engine.cu)
+int engine_create_single(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                         const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs,
+                         int ncones, const int* cone_type, const int* cone_dim, const cip_options* opts);
+const char* last_error_string();
+
+// ---- single-process multi-GPU front (multi.cu): same contracts as the C ABI entry points, global vectors
+int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,
+                 const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs, int ncones,
+                 const int* cone_type, const int* cone_dim, const cip_options* opts);
+int multi_destroy(cip_engine* h);
+int multi_factor(cip_engine* h, const int* kind, const double* fa, const double* fb, const double* fD,
+                 const double* fR, int factor);      // factor = 0: cip_set_scaling
+int multi_get_scaling(cip_engine* h, int* kind, double* fa, double* fb, double* fD, double* fR);
+int multi_nt_scaling(cip_engine* h, const double* v, const double* s, double* lambda_out, int factor);
+int multi_solve(cip_engine* h, const double* ry, const double* rw, const double* rv, double* dy, double* dw,
+                double* dv);
+int multi_apply(cip_engine* h, int op, const double* x, double* y);
+int multi_maxstep(cip_engine* h, const double* x, const double* d, double d_scale, double* alpha_out);
+int multi_prod_div(cip_engine* h, const double* x, const double* y, double* o, int divide);
+int multi_mul_A(cip_engine* h, int trans, const double* x, double* y);
+int multi_mul_GQ(cip_engine* h, int which, int trans, const double* x, double* y);   // which: 0 = G, 1 = Q
+int multi_ipm_solve(cip_engine* h, const double* c, const double* b, const double* d, const cip_ipm_options* opts,
+                    double* y, double* w, double* v, cip_ipm_result* result);
+int multi_stats(cip_engine* h, cip_stats_t* out);
+int multi_simple(cip_engine* h, int what, double* out, int ldo);   // 0 form_H, 1 factor_H, 2 sync, 3 get_H
+void multi_barrier(cip::Multi* m);   // rendezvous of the shard threads inside one dispatched call
 }  // namespace cip

@@ -204,7 +204,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                     CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
-bool g_attr_set = false;
+std::atomic<unsigned long long> g_attr_set{0};
 }  // namespace
 
 int gemm_nt_smem_bytes() { return SMEM_BYTES; }
@@ -237,25 +237,23 @@ int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long k
 }
 
 int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a, cudaStream_t stream) {
-  if (!g_attr_set) {
-    CIP_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_attr_set = true;
-  }
+  CIP_TRY(ensure_dyn_smem((const void*)gemm_nt_kernel, SMEM_BYTES, &g_attr_set));
+  const int nsm = sm_count();      // one CTA per SM (192 KB of shared memory each): a wave is nsm tiles
   const long long tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
   if (tiles <= 0 || a.nk <= 0) return 0;
   GemmArgs b = a;
   b.ksplit = 1;
   b.kchunk = a.nk;
   b.tail0 = (int)tiles;
-  const long long tail = tiles % 148;
+  const long long tail = tiles % nsm;
   if (a.ws && tail > 0 && a.nk >= 8) {
-    // cost of the tail in units of one full tile: ceil(tail * ks / 148) / ks  (+ the reduction pass: a split
+    // cost of the tail in units of one full tile: ceil(tail * ks / nsm) / ks  (+ the reduction pass: a split
     // costs about a quarter of one k tile); pick the cheapest ks that fits the workspace
     const long long cap = a.ws_doubles / (long long)(BM * BN);
     int best = 1;
     double best_cost = 1.0;
-    for (int ks = 2; ks <= 148 && ks <= a.nk / 4 && tail * ks <= cap; ++ks) {
-      const double cost = (double)((tail * ks + 147) / 148) / ks + 0.25 * ks / a.nk;
+    for (int ks = 2; ks <= nsm && ks <= a.nk / 4 && tail * ks <= cap; ++ks) {
+      const double cost = (double)((tail * ks + nsm - 1) / nsm) / ks + 0.25 * ks / a.nk;
       if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
     }
     if (best > 1) {

@@ -46,7 +46,9 @@ struct Ipm {
   cudaStream_t st;
   int n, m, p;
   std::vector<double*> pool;
-  double* scratch = nullptr;   // device [2*MAXP]
+  double* scratch = nullptr;   // device [4*MAXP]
+  double* dslot = nullptr;     // device [2*nranks]: step-length exchange across the row shards
+  std::vector<double> slot;
   int rc = 0;
 
   double* vec(size_t len) {
@@ -88,16 +90,15 @@ struct Ipm {
     if (h->comm) {
       // global min through the engine's sum all-reduce: every rank writes its two values into its own
       // slots of a zero vector (an all-gather), +Inf included (Inf + 0 = Inf stays in its slot)
-      std::vector<double> slot(2 * h->nranks, 0.0);
+      // (dslot is allocated once per solve: a cudaMalloc / cudaFree pair here would be an implicit device
+      //  synchronisation three times per iteration)
+      slot.assign(2 * h->nranks, 0.0);
       slot[2 * h->rank] = a1; slot[2 * h->rank + 1] = a2;
-      double* dslot = vec(2 * h->nranks);
       cudaMemcpyAsync(dslot, slot.data(), sizeof(double) * slot.size(), cudaMemcpyHostToDevice, st);
       ck(engine_allreduce(h, dslot, slot.size()));
       cudaMemcpyAsync(slot.data(), dslot, sizeof(double) * slot.size(), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
       for (int r = 0; r < h->nranks; ++r) { a1 = std::min(a1, slot[2 * r]); a2 = std::min(a2, slot[2 * r + 1]); }
-      cudaFree(dslot);
-      pool.pop_back();
     }
   }
   double gsum(double x) {     // scalar sum over ranks (setup only)
@@ -118,6 +119,7 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
                              const cip_ipm_options* opt_in, double* y_out, double* w_out, double* v_out,
                              cip_ipm_result* res) {
   if (!h || !res || !c_in || (h->m && !b_in) || (h->p && !d_in)) { set_error("cip_ipm_solve: null argument"); return -1; }
+  if (h->multi) return multi_ipm_solve(h, c_in, b_in, d_in, opt_in, y_out, w_out, v_out, res);
   CIP_CUDA(cudaSetDevice(h->device));
   const auto t_start = std::chrono::steady_clock::now();
   cip_ipm_options o{};
@@ -133,6 +135,7 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
   const int n = I.n, m = I.m, p = I.p;
   CIP_CUDA(cudaMalloc(&I.scratch, sizeof(double) * 4 * MAXP));
   I.pool.push_back(I.scratch);
+  if (h->comm) I.dslot = I.vec(2 * h->nranks);
 
   // ---- problem vectors, e and conedim (src/ConicIP.jl:547-565)
   double *c = I.vec(n), *b = I.vec(m), *d = I.vec(p), *e = I.vec(m), *ones = I.vec(m);
@@ -156,10 +159,12 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
   I.fill(ones, 1.0, m);
   conedim = I.gsum(conedim);
   const double m_glob = I.gsum((double)m);
+  const bool any_s = I.gsum((double)h->cd.ns) > 0;     // some shard holds S cones: their NT scaling can fail
 
   V4 z = I.v4(), rl = I.v4(), r0 = I.v4(), r = I.v4(), daff = I.v4(), dz = I.v4(), dzr = I.v4(), rI = I.v4();
   double *lam = I.vec(m), *t1 = I.vec(m), *tm1 = I.vec(m), *tm2 = I.vec(m), *lc = I.vec(m);
   double *Qy = I.vec(n), *Gtw = I.vec(n), *Atv = I.vec(n), *tn1 = I.vec(n), *Ay = I.vec(m), *tp1 = I.vec(p);
+  multi_barrier(h->parent);        // shard threads of one process: all allocations done before the first collective
   if (I.rc) return I.rc;
 
   const auto n0 = I.dots({{c, c, n}, {d, d, p}}, {{b, b, m}});
@@ -202,7 +207,9 @@ extern "C" int cip_ipm_solve(cip_handle h, const double* c_in, const double* b_i
   double yscale = 1.0, vwscale = 1.0;
 
   for (int Iter = 1; Iter <= o.maxIters && I.rc == 0; ++Iter) {
-    I.ck(cip_nt_scaling(h, z.v, z.s, lam));                           // :732-735
+    const int nst = cip_nt_scaling(h, z.v, z.s, lam);                 // :732-735
+    if (nst < 0) { I.ck(nst); break; }
+    if ((any_s ? I.gsum(nst > 0 ? 1.0 : 0.0) : (double)nst) > 0) { status = CIP_STATUS_ERROR; break; }                 // S-cone iterate not PD (PosDefException, :201)
     I.ck(cip_form_H(h));
     int fst = cip_factor_H(h);                                         // :737 -> :682
     ++factors;

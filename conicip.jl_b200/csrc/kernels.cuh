@@ -18,8 +18,10 @@ int unpack_rows_q4(double* dst, int ldd, const double* src, int ld, int R, int K
 int add_diag_q4(double* X, int ld, int from, int to, double val, int set, cudaStream_t s);
 int set_diag_vec_q4(double* X, int ld, int n, const double* v, cudaStream_t s);
 // device CSC arrays (colptr[ncols+1], rowval/nzval[nnz], index base 0 or 1) scattered into a zeroed Q4 matrix
+// Entries whose row index falls outside [0, nrows) are skipped and flagged: *bad = 1 + column (first one wins).
 int scatter_csc_q4(double* dst, int ld, int ncols, const long long* colptr, const long long* rowval,
-                   const double* nzval, int base, int transpose, cudaStream_t s);
+                   const double* nzval, int base, int transpose, int nrows, long long nnz, int* bad,
+                   cudaStream_t s);
 // dst[q4(j, k0 + i)] = scale * src[q4(i, j)]  for i < R, j < K   (G -> the augmentation rows of Atil)
 int transpose_scale_q4(double* dst, int ldd, int k0, const double* src, int lds, int R, int K, double scale,
                        cudaStream_t s);

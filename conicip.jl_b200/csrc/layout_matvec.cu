@@ -74,11 +74,17 @@ __global__ void set_diag_vec_kernel(double* X, int ld, int n, const double* __re
 // X[r=j,k=i] (transpose=1: A).  atomicAdd so duplicate entries sum, as in Julia's sparse().
 __global__ void scatter_csc_kernel(double* __restrict__ dst, int ld, const long long* __restrict__ colptr,
                                    const long long* __restrict__ rowval, const double* __restrict__ nzval,
-                                   int base, int transpose) {
+                                   int base, int transpose, int nrows, long long nnz, int* __restrict__ bad) {
   const int j = blockIdx.x;
   const long long e0 = colptr[j] - base, e1 = colptr[j + 1] - base;
+  if (e0 < 0 || e1 < e0 || e1 > nnz) {
+    if (threadIdx.x == 0) atomicCAS(bad, 0, j + 1);
+    return;
+  }
   for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-    const int i = (int)(rowval[e] - base);
+    const long long il = rowval[e] - base;
+    if (il < 0 || il >= nrows) { atomicCAS(bad, 0, j + 1); continue; }
+    const int i = (int)il;
     const size_t idx = transpose ? q4_index(j, i, ld) : q4_index(i, j, ld);
     atomicAdd(dst + idx, nzval[e]);
   }
@@ -217,9 +223,10 @@ int set_diag_vec_q4(double* X, int ld, int n, const double* v, cudaStream_t s) {
 }
 
 int scatter_csc_q4(double* dst, int ld, int ncols, const long long* colptr, const long long* rowval,
-                   const double* nzval, int base, int transpose, cudaStream_t s) {
+                   const double* nzval, int base, int transpose, int nrows, long long nnz, int* bad,
+                   cudaStream_t s) {
   if (ncols <= 0) return 0;
-  scatter_csc_kernel<<<ncols, 128, 0, s>>>(dst, ld, colptr, rowval, nzval, base, transpose);
+  scatter_csc_kernel<<<ncols, 128, 0, s>>>(dst, ld, colptr, rowval, nzval, base, transpose, nrows, nnz, bad);
   CIP_CHECK_LAUNCH();
   return 0;
 }
@@ -244,7 +251,7 @@ int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double*
   if (R <= 0) return 0;
   const int Kq = (K + 3) / 4;  // v must be readable (zero-padded) up to 4*Kq
   const int rblocks = (R + 127) / 128;
-  int nsplit = (148 * 8 + rblocks - 1) / rblocks;
+  int nsplit = (sm_count() * 8 + rblocks - 1) / rblocks;
   if (nsplit > Kq) nsplit = Kq > 0 ? Kq : 1;
   if ((long long)nsplit * R > partial_capacity) nsplit = partial_capacity / R;
   if (nsplit < 1) {
@@ -272,7 +279,7 @@ int q4_mv_k(double* out, const double* X, int ld, int R, int K, const double* u,
 int vec_axpby(double* out, double a, const double* x, double b, const double* y, size_t n, cudaStream_t s) {
   if (n == 0) return 0;
   int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   axpby_kernel<<<blocks, 256, 0, s>>>(out, a, x, b, y, n);
   CIP_CHECK_LAUNCH();
   return 0;

@@ -19,6 +19,11 @@ struct NcclApi {
                    cudaStream_t stream) = nullptr;
   int (*Broadcast)(const void* send, void* recv, size_t count, int dtype, int root, void* comm,
                    cudaStream_t stream) = nullptr;
+  int (*CommInitAll)(void** comms, int ndev, const int* devlist) = nullptr;
+  int (*Reduce)(const void* send, void* recv, size_t count, int dtype, int op, int root, void* comm,
+                cudaStream_t stream) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void* comm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };

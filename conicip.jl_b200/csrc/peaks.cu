@@ -48,7 +48,7 @@ int measure_fp64_peaks(double* dmma_tflops, double* dfma_tflops) {
   cudaEvent_t e0, e1;
   CIP_CUDA(cudaEventCreate(&e0));
   CIP_CUDA(cudaEventCreate(&e1));
-  const int blocks = 148 * 4;
+  const int blocks = sm_count() * 4;
   double best_mma = 0.0, best_fma = 0.0;
   for (int iters : {4096}) {
     for (int rep = 0; rep < 5; ++rep) {

@@ -231,7 +231,7 @@ int imcols_impl(int device, const double* A, int lda, int p, int n, const double
     return 0;
   }
   const double thresh = eps * fro;           // |R_kk| / ||A||_F > eps   <=>   r_kk > eps ||A||_F
-  const int qblocks = std::max(1, std::min(148 * 4, (n + 255) / 256));
+  const int qblocks = std::max(1, std::min(sm_count() * 4, (n + 255) / 256));
   for (int k = 0; k < kmax; ++k) {
     mc_pivot_kernel<<<1, 256, 0, B.s>>>(B.norms2, B.used, p, thresh * thresh, B.st, B.order);
     CIP_CHECK_LAUNCH();

@@ -252,7 +252,13 @@ sdp_nt_kernel(SDesc d, int* __restrict__ kindF, int* __restrict__ kindFi, double
   const int ok2 = *s.flag;
   __syncthreads();
   if (!(ok1 && ok2)) {
-    if (threadIdx.x == 0) atomicCAS(info, 0, ci + 1);
+    // mat(s) or mat(z) is not positive definite: the reference throws PosDefException from cholesky(mat(s))
+    // here (src/ConicIP.jl:201-202).  Flag the cone (read back by cip_nt_scaling, which returns ci + 1), poison
+    // lambda so that nothing downstream can use the half-factored matrices, and stop.
+    if (threadIdx.x == 0) { atomicCAS(info, 0, ci + 1); kindF[ci] = CIP_BLK_VECCONG; kindFi[ci] = CIP_BLK_VECCONG; }
+    const int dim = k * (k + 1) / 2;
+    for (int e = threadIdx.x; e < dim; e += NT) lambda[off + e] = CUDART_NAN;
+    return;
   }
   matmul<true, false>(s.C, s.B, s.A, k);   // G = Lz' Ls
   __syncthreads();
@@ -464,16 +470,12 @@ sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __re
   (void)dim;
 }
 
-bool g_attr = false;
+std::atomic<unsigned long long> g_attr[6];
 int set_attrs() {
-  if (g_attr) return 0;
-  CIP_CUDA(cudaFuncSetAttribute(sdp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  CIP_CUDA(cudaFuncSetAttribute(sdp_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  CIP_CUDA(cudaFuncSetAttribute(sdp_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  CIP_CUDA(cudaFuncSetAttribute(sdp_prod_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  CIP_CUDA(cudaFuncSetAttribute(sdp_maxstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  CIP_CUDA(cudaFuncSetAttribute(sdp_scale_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDP_SMEM));
-  g_attr = true;
+  const void* fn[6] = {(const void*)sdp_apply_kernel, (const void*)sdp_nt_kernel, (const void*)sdp_invert_kernel,
+                       (const void*)sdp_prod_div_kernel, (const void*)sdp_maxstep_kernel,
+                       (const void*)sdp_scale_panel_kernel};
+  for (int i = 0; i < 6; ++i) CIP_TRY(ensure_dyn_smem(fn[i], SDP_SMEM, &g_attr[i]));
   return 0;
 }
 SDesc sdesc(const ConeDesc& c) { return SDesc{c.slist, c.off, c.sord, c.roff}; }

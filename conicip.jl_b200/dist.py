@@ -14,7 +14,7 @@ def shard_cones(cone_dims, nranks):
     for t, k in cone_dims:
         pieces.append((t, int(k)))
     m = sum(k for _, k in pieces)
-    targets = [round(m * (r + 1) / nranks) for r in range(nranks)]
+    targets = [int(np.floor(m * (r + 1) / nranks + 0.5)) for r in range(nranks)]   # == llround in cip_shard_plan
     out, row, cur, lo, r = [], 0, [], 0, 0
     for t, k in pieces:
         while k > 0:

@@ -36,7 +36,7 @@ class Engine:
     """LEVEL-1 object: `kktsolver(Q, A, G, cone_dims)` (src/ConicIP.jl:667)."""
 
     def __init__(self, Q, A, G, cone_dims, *, reg_delta=0.0, reg_eps_G=0.0, device=-1,
-                 use_torch_stream=True, dist_chol=-1, aug_rho=-1.0):
+                 use_torch_stream=True, dist_chol=-1, aug_rho=-1.0, ngpus=1):
         L = lib()
         self.cone_dims = [(t, int(k)) for t, k in cone_dims]
         self.cone_type = np.array([CONE_CODE[t] for t, _ in self.cone_dims], dtype=np.int32)
@@ -52,6 +52,8 @@ class Engine:
         opts.q_kind = 0
         opts.dist_chol = dist_chol
         opts.aug_rho = aug_rho
+        opts.ngpus = int(ngpus)            # > 1: single-process multi-GPU handle (global vectors in and out)
+        self.ngpus = max(1, int(ngpus))
         self._torch = None
         self._use_torch_stream = use_torch_stream
         self.last_factor_status = 0
@@ -105,7 +107,9 @@ class Engine:
             if self._G.shape[1] != n and p > 0:
                 raise ValueError("Inconsistency in equalities/objective")
             if _is_torch(self._G):
-                g_ptr, ldg = self._G.data_ptr(), self._G.stride(1)
+                if p > 1 and self._G.stride(0) != 1:
+                    raise ValueError("device G must be column-major: pass X.t() of a contiguous (n, p) tensor")
+                g_ptr, ldg = self._G.data_ptr(), (self._G.stride(1) if n > 1 else p)
             else:
                 g_ptr, ldg = (self._G.ctypes.data if p else None), max(p, 1)
 
@@ -168,7 +172,10 @@ class Engine:
         if self._torch is None:
             import torch
             self._torch = torch
-        if self._use_torch_stream:
+        if self.ngpus > 1:
+            # one stream per device inside the handle: device inputs must be complete before the call
+            self._torch.cuda.current_stream().synchronize()
+        elif self._use_torch_stream:
             check(lib().cip_set_stream(self._h, self._torch.cuda.current_stream().cuda_stream))
 
     def _ptr(self, x, length):
@@ -272,7 +279,9 @@ class Engine:
     def nt_scaling(self, v, s):
         dev, (v, s) = self._prep(v, s)
         lam = self._new(dev, self.m)
-        check(lib().cip_nt_scaling(self._h, self._ptr(v, self.m), self._ptr(s, self.m), self._ptr(lam, self.m)))
+        rc = check(lib().cip_nt_scaling(self._h, self._ptr(v, self.m), self._ptr(s, self.m), self._ptr(lam, self.m)))
+        if rc > 0:      # S-cone iterate not positive definite: PosDefException in the reference (src/ConicIP.jl:201-202)
+            raise _lib.CipError(rc, _lib.last_error())
         return lam
 
     def apply(self, op, x):
@@ -360,6 +369,15 @@ class Engine:
 
     def sync(self):
         check(lib().cip_sync(self._h))
+
+
+def shard_plan(cone_dims, ngpus):
+    """Row ranges [(lo, hi)] a handle with `ngpus` devices gives its shards (`cip_shard_plan`, host logic)."""
+    ct = np.array([CONE_CODE[t] for t, _ in cone_dims], dtype=np.int32)
+    cd = np.array([int(k) for _, k in cone_dims], dtype=np.int32)
+    lo, hi = np.zeros(ngpus, dtype=np.int32), np.zeros(ngpus, dtype=np.int32)
+    check(lib().cip_shard_plan(len(cd), ct.ctypes.data, cd.ctypes.data, int(ngpus), lo.ctypes.data, hi.ctypes.data))
+    return [(int(a), int(b)) for a, b in zip(lo, hi)]
 
 
 def nccl_unique_id():

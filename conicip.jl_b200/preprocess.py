@@ -50,9 +50,15 @@ def imcols(A, b, eps=1e-8, device=-1):
     return np.flatnonzero(keep[:p]).astype(np.int64), True
 
 
-def preprocess_conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, verbose=False, native=True, **options):
+def preprocess_conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, verbose=False, native=True,
+                       dual_check="auto", **options):
     """src/preprocessor.jl:40-96.  `native=True` solves with `cip_ipm_solve`, else with the Python host driver
-    (which accepts `kktsolver=`)."""
+    (which accepts `kktsolver=`).
+
+    `dual_check`: the reference always runs the dual rank check on [Q A' G'] (:59) and augments Q + Z.  Above
+    DUAL_CHECK_MAX_ELEMS matrix elements the dense working copy of that check does not fit comfortably, so
+    "auto" skips it there WITH a `RuntimeWarning` (a rank-deficient dual can then end in Error where the
+    reference reaches Optimal); True forces the check at any size, False never runs it."""
     c = np.asarray(c, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     n, m = len(c), len(b)
@@ -61,10 +67,14 @@ def preprocess_conicIP(Q, c, A, b, cone_dims, G=None, d=None, *, verbose=False, 
     p = Gd.shape[0]
     IP, pcons = imcols(Gd, d)                                       # :58
     dcons, ID = True, np.arange(n)
-    if n * (n + m + len(IP)) <= DUAL_CHECK_MAX_ELEMS:
+    small = n * (n + m + len(IP)) <= DUAL_CHECK_MAX_ELEMS
+    if dual_check is True or (dual_check == "auto" and small):
         ID, dcons = imcols(np.hstack([_dense(Q), _dense(A).T, Gd[IP, :].T]), c)     # :59
-    elif verbose:
-        print("   - dual rank check skipped (matrix too large); assuming rank([Q A' G']) = n")
+    elif dual_check == "auto":
+        import warnings
+        warnings.warn(f"preprocess_conicIP: dual rank check on the {n} x {n + m + len(IP)} matrix [Q A' G'] skipped "
+                      "(too large); assuming full rank.  Pass dual_check=True to force it as the reference does "
+                      "(src/preprocessor.jl:59).", RuntimeWarning, stacklevel=2)
     if not (pcons and dcons):                                       # :61-64
         return Solution(np.full(n, np.nan), np.full(p, np.nan), np.full(m, np.nan), status="Infeasible")
     if verbose:

@@ -154,7 +154,8 @@ def config4_device(n=16384, m=262144, seed=4, rank=0, nranks=1, scale_rows=None)
     """C4 -- large dense QP generated directly on the device, row-sharded: this rank's slab
     holds rows [rank*m/nranks, (rank+1)*m/nranks).  Rows are drawn from a per-row-block
     Philox stream so every sharding sees the same global matrix.
-    Returns torch tensors: At (n x m_local, contiguous => column-major A slab), b, Q(diag), c."""
+    Returns torch tensors: At (n x m_local, contiguous => column-major A slab), b, Q (dense, symmetric; `qdiag` is
+    its diagonal part), c."""
     import torch
     m_loc = m // nranks
     r0 = rank * m_loc
@@ -169,8 +170,13 @@ def config4_device(n=16384, m=262144, seed=4, rank=0, nranks=1, scale_rows=None)
     y0 = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
     c = torch.randn(n, generator=g, dtype=torch.float64, device="cuda")
     qdiag = 1.0 + torch.rand(n, generator=g, dtype=torch.float64, device="cuda")
+    # Q = diag(U(1,2)) + U U' with U n x 32 N(0,1)/sqrt(32), "as C2" 
+    U = torch.randn((n, 32), generator=g, dtype=torch.float64, device="cuda") / (32 ** 0.5)
+    Q = U @ U.t()
+    Q.diagonal().add_(qdiag)
+    del U
     gs = torch.Generator(device="cuda")
     gs.manual_seed(seed * 7919 + 13)
     s0_full = 0.1 + torch.rand(m, generator=gs, dtype=torch.float64, device="cuda")
     b = At.t() @ y0 - s0_full[r0:r0 + m_loc]
-    return dict(name="C4", At=At, b=b, qdiag=qdiag, c=c, cone_dims=[("R", m_loc)], n=n, m=m, m_loc=m_loc)
+    return dict(name="C4", At=At, b=b, qdiag=qdiag, Q=Q, c=c, cone_dims=[("R", m_loc)], n=n, m=m, m_loc=m_loc)

@@ -60,6 +60,12 @@ typedef struct cip_options {
   double aug_rho;       /* equality block: factor H + rho*G'G (and add rho*G'rw to the rhs) so that H may be
                            singular on range(G') as kktsolver_qr allows (src/kktsolvers.jl:35); same solution.
                            < 0: auto (1.0 when p > 0), 0: off */
+  int    ngpus;         /* single-process multi-GPU (SURVEY 8b "Threading", 8e): > 1 slices the rows of A on cone
+                           boundaries over the devices device .. device+ngpus-1 (0 .. ngpus-1 when device < 0), one
+                           stream and one NCCL communicator per device (ncclCommInitAll), all driven from the
+                           calling thread's single call -- the reference calls its kktsolver once from one process
+                           (src/ConicIP.jl:667), so this is what `kktsolver = kktsolver_b200(ngpus = 8)` uses.
+                           Every entry point below then takes and returns GLOBAL vectors; 0 / 1 = one device */
 } cip_options;
 
 typedef struct cip_stats_t {
@@ -103,11 +109,16 @@ int cip_create_csc(cip_handle* out, int n, const cip_csc* Q, const cip_csc* A, c
                    int ncones, const int* cone_type, const int* cone_dim, const cip_options* opts);
 int cip_destroy(cip_handle h);
 
-/* Row-sharded multi-GPU (no counterpart in the reference): one
+/* Row-sharded multi-GPU across PROCESSES (no counterpart in the reference; the
+ * single-process form is cip_options.ngpus): one
  * process per GPU, each created with its own row slab of A.  The 128-byte NCCL
  * unique id is produced on rank 0 and distributed by the host (torch.distributed,
  * MPI, Julia Distributed ...).  After this call cip_factor all-reduces the
  * partial Gram matrices and cip_solve all-reduces A'*(W^-2 v). */
+/* How a handle with opts.ngpus = N slices the rows of A (pure host logic, no device needed): contiguous
+ * cone-aligned slabs of near-equal size; R cones may be cut anywhere (W is diagonal there), Q / S cones never.
+ * row_lo / row_hi [ngpus] out: shard r owns the global rows [row_lo[r], row_hi[r]).  Returns 0 or -1. */
+int cip_shard_plan(int ncones, const int* cone_type, const int* cone_dim, int ngpus, int* row_lo, int* row_hi);
 int cip_nccl_unique_id(unsigned char id_out[128]);
 int cip_comm_init(cip_handle h, int nranks, int rank, const unsigned char id[128]);
 

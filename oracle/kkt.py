@@ -154,3 +154,47 @@ def kktsolver_chol(Q, A, G, cone_dims):
         return solve3x3
 
     return solve3x3gen
+
+
+class SlabbedCholKKT:
+    """`kktsolver_chol` for K = R^m with A streamed in row slabs (the C4 shape, 34 GB, is never held on the
+    host at once): the same arithmetic and the same BLAS/LAPACK routines Julia's LinearAlgebra dispatches to,
+    slab by slab.  Used by bench.py's CPU legs (and pinned to `kktsolver_chol` by tests/test_oracle_units.py).
+
+      add_rows   Atil = F^-T*A (src/kktsolvers.jl:33);  H += Atil'Atil -> BLAS dsyrk (:34; `syrk_wrapper!`)
+      factor     cholesky(Q + H) -> LAPACK dpotrf      (stands in for qr(Q2'HQ2) :35 / lu([H G';G 0]) :295)
+      rhs_rows   t1 = F^-T F^-T v;  y + A't1           (:326-327, slab share of the GEMV)
+      solve      L \\ . , L' \\ .   -> dtrsv            (:299)
+      dv_rows    t1 - F^-T F^-T (A dy)                 (:328, slab share of the GEMV)
+    """
+
+    def __init__(self, n, q_diag):
+        self.n = n
+        self.q_diag = np.asarray(q_diag, dtype=np.float64)
+        self.H = np.zeros((n, n), order="F")
+        self.L = None
+
+    def add_rows(self, A_slab, f_slab):
+        Atil = A_slab * (1.0 / f_slab)[:, None]                    # F^-T A, F = Diagonal(f)
+        # Atil is C-ordered (rows x n): its transpose view is the Fortran-ordered n x rows matrix X, H += X X'
+        self.H = sla.blas.dsyrk(1.0, Atil.T, beta=1.0, c=self.H, trans=0, lower=1, overwrite_c=1)
+
+    def factor(self):
+        Hq = self.H
+        Hq[np.diag_indices(self.n)] += self.q_diag
+        self.L = sla.cholesky(Hq, lower=True, check_finite=False, overwrite_a=True)
+        self.H = None
+        return self.L
+
+    @staticmethod
+    def rhs_rows(A_slab, f_slab, v_slab):
+        t1 = v_slab / (f_slab * f_slab)
+        return t1, A_slab.T @ t1
+
+    def solve(self, rhs):
+        t = sla.solve_triangular(self.L, rhs, lower=True, check_finite=False)
+        return sla.solve_triangular(self.L, t, lower=True, trans="T", check_finite=False)
+
+    @staticmethod
+    def dv_rows(A_slab, f_slab, t1, dy):
+        return t1 - (A_slab @ dy) / (f_slab * f_slab)

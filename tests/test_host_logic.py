@@ -170,3 +170,26 @@ def test_imcols_paths_that_need_no_device():
     assert rc == -2 and "cip_imcols" in last_error()
     with pytest.raises(ValueError):
         cb.imcols(np.zeros((3, 2)), np.zeros(5))
+
+
+def test_shard_plan_matches_python_mirror():
+    """`cip_shard_plan` (what a handle with opts.ngpus = N does to the rows of A) is pure host logic and must
+    agree with the Python mirror used by the one-process-per-GPU path (`dist.shard_cones`)."""
+    import conicip_b200 as cb
+    from conicip_b200.dist import shard_cones
+    cases = [[("R", 1000)], [("R", 7)], [("Q", 33)] * 64, [("R", 80)] + [("Q", 9)] * 6,
+             [("R", 20000), ("S", 2080)], [("Q", 5), ("R", 100), ("S", 21), ("Q", 40), ("R", 3)]]
+    for cd in cases:
+        m = sum(k for _, k in cd)
+        for N in (1, 2, 3, 4, 8):
+            plan = cb.shard_plan(cd, N)
+            want = [(lo, hi) for lo, hi, _ in shard_cones(cd, N)]
+            assert plan == want, (cd[:3], N, plan, want)
+            assert plan[0][0] == 0 and plan[-1][1] == m
+            assert all(plan[i][1] == plan[i + 1][0] for i in range(N - 1))
+            # Q / S cones are never cut
+            off = 0
+            for t, k in cd:
+                if t != "R":
+                    assert any(lo <= off and off + k <= hi for lo, hi in plan), (t, k, plan)
+                off += k

@@ -110,3 +110,33 @@ def test_cone_kernel_fixture():
     assert np.allclose(W.B, g["nestod_soc_w"], rtol=1e-13) and np.allclose(W.Adiag, g["nestod_soc_diag"], rtol=1e-13)
     assert np.allclose(g["lam"], g["lam_alt"], rtol=1e-10)
     assert O.maxstep_soc(z, d) == pytest.approx(g["maxstep_soc"], rel=1e-13)
+
+
+def test_slabbed_chol_kkt_equals_kktsolver_chol():
+    """bench.py's CPU leg streams A in row slabs (C4 never fits the host twice); it must be the same
+    solver as `kktsolver_chol` on the same data."""
+    import oracle as O
+    from oracle.kkt import SlabbedCholKKT
+    rng = np.random.default_rng(11)
+    n, m = 40, 90
+    A = rng.standard_normal((m, n))
+    q = rng.uniform(1, 2, n)
+    f = rng.uniform(0.5, 2, m)
+    ry, rv = rng.standard_normal(n), rng.standard_normal(m)
+    F = O.Block([O.Diag(f)])
+    solve = O.kktsolver_chol(np.diag(q), A, np.zeros((0, n)), [("R", m)])(F, F.inv())
+    dy0, _, dv0 = solve(ry, np.zeros(0), rv)
+    K = SlabbedCholKKT(n, q)
+    slabs = [(0, 32), (32, 64), (64, 90)]
+    for lo, hi in slabs:
+        K.add_rows(A[lo:hi], f[lo:hi])
+    K.factor()
+    rhs, t1s = ry.copy(), []
+    for lo, hi in slabs:
+        t1, g = K.rhs_rows(A[lo:hi], f[lo:hi], rv[lo:hi])
+        t1s.append(t1)
+        rhs += g
+    dy = K.solve(rhs)
+    dv = np.concatenate([K.dv_rows(A[lo:hi], f[lo:hi], t1, dy) for (lo, hi), t1 in zip(slabs, t1s)])
+    assert np.linalg.norm(dy - dy0) <= 1e-12 * np.linalg.norm(dy0)
+    assert np.linalg.norm(dv - dv0) <= 1e-12 * np.linalg.norm(dv0)

@@ -91,6 +91,7 @@ SIGNATURES = {
     "cip_get_H": (C.c_int, [C.c_void_p, _P, C.c_int]),
     "cip_form_H": (C.c_int, [C.c_void_p]),
     "cip_factor_H": (C.c_int, [C.c_void_p]),
+    "cip_solve_H": (C.c_int, [C.c_void_p, _P, _P]),
     "cip_sync": (C.c_int, [C.c_void_p]),
     "cip_stream": (C.c_void_p, [C.c_void_p]),
     "cip_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),

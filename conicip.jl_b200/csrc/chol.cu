@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "kernels.cuh"
 #include "nccl_dl.h"
 
@@ -512,113 +515,207 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
 #endif
 }
 
-// forward sweep step for panel jb:  y_j = inv(L_jj) b_j ;  b_i -= L_ij y_j  (i > j)
-// 512 threads: thread (row r, part) handles 8 of the 32 k-quads so that all 16 loads are in flight.
-__global__ void __launch_bounds__(512)
-trsv_fwd_kernel(const double* __restrict__ H, int ld, const double* __restrict__ Winv, int jb,
-                double* __restrict__ b, double* __restrict__ y) {
-  __shared__ double bj[NB], yj[NB], red[4][NB];
-  const int tid = threadIdx.x, j0 = jb * NB;
-  const int r = tid & 127, part = tid >> 7;
-  if (tid < NB) bj[tid] = b[j0 + tid];
-  __syncthreads();
-  {
-    const double* W = Winv + (size_t)jb * NB * NB;
-    double2 w[16];
+// ---------------------------------------------------------------- triangular sweeps (K3)
+// One persistent launch per direction (forward L y = b, backward L' x = y) instead of one launch per
+// 128-column panel.  Block row b of the triangular matrix is owned by CTAs ("units"): its off-diagonal tiles
+// are cut into segments of at most `seg` tiles, one unit per segment; every unit streams its 128x128 tiles
+// (coalesced 32-byte loads, the next half tile always in flight) and multiplies them with the solution blocks
+// as those are PUBLISHED by the units that own them; the unit that holds the last tile of the row (the
+// "finisher") adds the partial sums of the other segments in segment order (deterministic), applies the stored
+// inverse of the diagonal block (already waiting in shared memory) and publishes its solution block.
+//   hand-off: every published double is self-validating.  Output and partial-sum buffers are preset to the
+//   all-ones bit pattern (a NaN that no arithmetic produces: results are canonicalised before they are stored)
+//   and consumers poll the value itself, so a hand-off costs ONE L2 round trip, no flag + data pair, no fence.
+//   no deadlock: units are ordered by the last solution block they need, so a unit only ever waits for units
+//   with a smaller index, which the hardware dispatches first; every poll also gives up after ~2^26 tries and
+//   raises *err, so that a bug cannot hang the device.
+// The chain per block row is: poll (1 L2 trip) -> 128x128 product from registers -> partials -> 128x128 product
+// with the inverse from shared memory -> publish; everything else (HBM streaming of L, once per sweep) hides
+// behind it.  Replaces `Z\[dy;dw]` at src/kktsolvers.jl:299 (LAPACK / UMFPACK triangular solves).
+constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_SMEM = NB * NB * (int)sizeof(double);      // inverse of the diagonal block
+constexpr unsigned long long SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+constexpr int SPIN_LIMIT = 1 << 26;
+
+struct SweepUnit { int blk, d0, nd, seg, nseg, fin; };   // block row, first dependency, #dependencies (in sweep order)
+
+__device__ __forceinline__ double canon(double v) {           // never store the sentinel bit pattern
+  return (v != v) ? __longlong_as_double(0x7FF8000000000000ll) : v;
+}
+__device__ __forceinline__ void publish(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(canon(v)) : "memory");
+}
+__device__ __forceinline__ double poll(const double* p, int* err) {
+  unsigned long long v;
+  int spins = 0;
+  do {
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v != SENTINEL) break;
+    if (++spins > SPIN_LIMIT) { atomicExch(err, 1); v = 0x7FF8000000000000ull; break; }
+  } while (true);
+  return __longlong_as_double((long long)v);
+}
+
+// FWD: sol = y, rhs = b:  y_b = inv(L_bb) (b_b - sum_{d<b} L_bd y_d),        dependencies d ascending
+// BWD: sol = x, rhs = y:  x_b = inv(L_bb)' (y_b - sum_{d>b} L_db' x_d),      dependencies d descending
+template <bool FWD>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+trsv_sweep_kernel(const double* __restrict__ H, int ld, const double* __restrict__ Winv,
+                  const SweepUnit* __restrict__ units, const double* __restrict__ rhs, double* sol,
+                  double* part, int maxseg, int* err) {
+  extern __shared__ __align__(16) double Ws[];                 // [32 quads][128 rows][4]: inv(L_bb), Q4 with ld = 128
+  __shared__ double vs[NB];                                    // the dependency's solution block
+  __shared__ double red[4][NB];
+  __shared__ double tot[NB];
+  const SweepUnit u = units[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (u.fin) {
+    // inverse of the diagonal block -> shared memory, asynchronously (needed only at the very end)
+    const double* W = Winv + (size_t)u.blk * NB * NB;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double2* p = reinterpret_cast<const double2*>(W + ((size_t)(part * 8 + i) * NB + r) * 4);
-      w[2 * i] = __ldg(p);
-      w[2 * i + 1] = __ldg(p + 1);
+    for (int i = 0; i < (NB * NB * 8) / (SWEEP_THREADS * 16); ++i) {
+      const int o = (i * SWEEP_THREADS + tid) * 2;             // doubles
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(Ws + o)), "l"(W + o) : "memory");
     }
-    double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double* bq = bj + 4 * (part * 8 + i);
-      acc = fma(w[2 * i].x, bq[0], acc); acc = fma(w[2 * i].y, bq[1], acc);
-      acc = fma(w[2 * i + 1].x, bq[2], acc); acc = fma(w[2 * i + 1].y, bq[3], acc);
-    }
-    red[part][r] = acc;
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __syncthreads();
-  if (tid < NB) yj[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    if (tid < NB) y[j0 + tid] = yj[tid];
-    return;
-  }
-  const int row = (jb + blockIdx.x) * NB + r;
-  {
-    double2 l[16];
+  // thread -> (row or quad, part) of a 128x128 tile; `base` = first 32-byte element of this thread in tile 0 of
+  // the row, `tstep` = distance between consecutive dependencies' tiles
+  //   FWD: tile(b, d) = rows 128b.., k-quads 32d..      thread (r = tid & 127, pq = tid >> 7): quads pq*8 .. +7
+  //   BWD: tile(d, b) = rows 128d.., k-quads 32b..      thread (q = tid >> 4, pr = tid & 15): rows pr + 16 i
+  const int r = tid & 127, pq = tid >> 7, q = tid >> 4, pr = tid & 15;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  double2 cur[8], nxt[8];
+  auto tile_ptr = [&](int d, int half) -> const double2* {
+    if (FWD) return reinterpret_cast<const double2*>(H + ((size_t)(d * 32 + pq * 8 + half * 4) * ld + (size_t)u.blk * NB + r) * 4);
+    return reinterpret_cast<const double2*>(H + ((size_t)(u.blk * 32 + q) * ld + (size_t)d * NB + pr + 64 * half) * 4);
+  };
+  auto load_half = [&](double2 (&buf)[8], int d, int half) {
+    const double2* p = tile_ptr(d, half);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + part * 8 + i) * ld + row) * 4);
-      l[2 * i] = __ldg(p);
-      l[2 * i + 1] = __ldg(p + 1);
+    for (int i = 0; i < 4; ++i) {
+      const size_t o = FWD ? (size_t)i * ld * 2 : (size_t)i * 32;      // in double2: next quad / 16 rows further
+      buf[2 * i] = __ldg(p + o);
+      buf[2 * i + 1] = __ldg(p + o + 1);
     }
-    double acc = 0.0;
+  };
+  auto fma_half = [&](const double2 (&buf)[8], int half) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double* yq = yj + 4 * (part * 8 + i);
-      acc = fma(l[2 * i].x, yq[0], acc); acc = fma(l[2 * i].y, yq[1], acc);
-      acc = fma(l[2 * i + 1].x, yq[2], acc); acc = fma(l[2 * i + 1].y, yq[3], acc);
+    for (int i = 0; i < 4; ++i) {
+      if (FWD) {
+        const double* v = vs + 4 * (pq * 8 + half * 4 + i);
+        a0 = fma(buf[2 * i].x, v[0], a0); a1 = fma(buf[2 * i].y, v[1], a1);
+        a2 = fma(buf[2 * i + 1].x, v[2], a2); a3 = fma(buf[2 * i + 1].y, v[3], a3);
+      } else {
+        const double v = vs[pr + 64 * half + 16 * i];
+        a0 = fma(buf[2 * i].x, v, a0); a1 = fma(buf[2 * i].y, v, a1);
+        a2 = fma(buf[2 * i + 1].x, v, a2); a3 = fma(buf[2 * i + 1].y, v, a3);
+      }
     }
+  };
+  const int dstep = FWD ? 1 : -1;
+  // finisher, off the chain: its right-hand side block and (before the last dependency is awaited) the partial
+  // sums of the other segments of the row, which were published long ago
+  double myrhs = 0.0, sib = 0.0;
+  if (u.fin && tid < NB) myrhs = rhs[(size_t)u.blk * NB + tid];
+  auto gather_siblings = [&]() {
+    if (!(u.fin && tid < NB)) return;
+    const double* pp = part + (size_t)u.blk * maxseg * NB + tid;
+    for (int sg = 0; sg < u.nseg - 1; sg += 4) {
+      // four independent loads in flight, then the (normally not taken) wait for those that were not there yet
+      unsigned long long w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = 0;
+        if (sg + k < u.nseg - 1)
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[k]) : "l"(pp + (size_t)(sg + k) * NB) : "memory");
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (sg + k < u.nseg - 1) {
+          const double v = (w[k] == SENTINEL) ? poll(pp + (size_t)(sg + k) * NB, err) : __longlong_as_double((long long)w[k]);
+          sib += v;                                             // segment order: deterministic
+        }
+      }
+    }
+  };
+  if (u.nd == 0) gather_siblings();
+  if (u.nd > 0) load_half(cur, u.d0, 0);
+  for (int t = 0; t < u.nd; ++t) {
+    const int d = u.d0 + t * dstep;
+    load_half(nxt, d, 1);
+    if (t == u.nd - 1) gather_siblings();
+    if (tid < NB) vs[tid] = poll(sol + (size_t)d * NB + tid, err);
     __syncthreads();
-    red[part][r] = acc;
+    fma_half(cur, 0);
+    if (t + 1 < u.nd) load_half(cur, d + dstep, 0);
+    fma_half(nxt, 1);
+    __syncthreads();                                           // vs is rewritten in the next round
   }
-  __syncthreads();
-  if (tid < NB) b[row] -= (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-}
-
-// backward sweep step for panel jb:  x_j = inv(L_jj)' y_j ;  y_i -= L_ji' x_j  (i < j)
-// 512 threads: 16 lanes share one k-quad (4 output columns) and split the 128 rows.
-__device__ __forceinline__ void colsum4(const double* __restrict__ base, const double* __restrict__ vec, int part,
-                                        double& a0, double& a1, double& a2, double& a3) {
-  double2 m[16];
+  // ---- reduce the partial sums of this unit to one value per row (FWD) / column (BWD) of the block
+  if (FWD) {
+    red[pq][r] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (tid < NB) tot[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    if (u.fin && tid < NB) vs[tid] = myrhs - (sib + tot[tid]);
+  } else {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double2* p = reinterpret_cast<const double2*>(base + (size_t)(part + 16 * i) * 4);
-    m[2 * i] = __ldg(p);
-    m[2 * i + 1] = __ldg(p + 1);
+    for (int o = 1; o <= 8; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (pr == 0) { tot[4 * q] = a0; tot[4 * q + 1] = a1; tot[4 * q + 2] = a2; tot[4 * q + 3] = a3; }
   }
-  a0 = a1 = a2 = a3 = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double vr = vec[part + 16 * i];
-    a0 = fma(m[2 * i].x, vr, a0); a1 = fma(m[2 * i].y, vr, a1);
-    a2 = fma(m[2 * i + 1].x, vr, a2); a3 = fma(m[2 * i + 1].y, vr, a3);
-  }
-#pragma unroll
-  for (int o = 1; o <= 8; o <<= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-  }
-}
-
-__global__ void __launch_bounds__(512)
-trsv_bwd_kernel(const double* __restrict__ H, int ld, const double* __restrict__ Winv, int jb,
-                double* __restrict__ y, double* __restrict__ x) {
-  __shared__ double yj[NB], xj[NB];
-  const int tid = threadIdx.x, j0 = jb * NB;
-  const int q = tid >> 4, part = tid & 15;
-  if (tid < NB) yj[tid] = y[j0 + tid];
+  if (u.fin) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  double a0, a1, a2, a3;
-  colsum4(Winv + (size_t)jb * NB * NB + (size_t)q * NB * 4, yj, part, a0, a1, a2, a3);
-  if (part == 0) { xj[4 * q] = a0; xj[4 * q + 1] = a1; xj[4 * q + 2] = a2; xj[4 * q + 3] = a3; }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    if (tid < NB) x[j0 + tid] = xj[tid];
+  double* mypart = part + ((size_t)u.blk * maxseg + u.seg) * NB;
+  if (!u.fin) {
+    if (tid < NB) publish(mypart + tid, tot[tid]);
     return;
   }
-  const int ib = blockIdx.x - 1;
-  colsum4(H + ((size_t)(ib * 32 + q) * ld + j0) * 4, xj, part, a0, a1, a2, a3);
-  if (part == 0) {
-    double* yo = y + ib * NB + 4 * q;
-    yo[0] -= a0; yo[1] -= a1; yo[2] -= a2; yo[3] -= a3;
+  // ---- finisher: rhs - (other segments in segment order + its own); inverse of the diagonal block
+  if (!FWD) {
+    if (tid < NB) vs[tid] = myrhs - (sib + tot[tid]);
+    __syncthreads();
+  }
+  if (FWD) {
+    // y[r] = sum_c W[r, c] v[c]
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int qq = pq * 8 + i;
+      const double2 w0 = *reinterpret_cast<const double2*>(Ws + ((size_t)qq * NB + r) * 4);
+      const double2 w1 = *reinterpret_cast<const double2*>(Ws + ((size_t)qq * NB + r) * 4 + 2);
+      const double* v = vs + 4 * qq;
+      s0 = fma(w0.x, v[0], s0); s1 = fma(w0.y, v[1], s1); s2 = fma(w1.x, v[2], s2); s3 = fma(w1.y, v[3], s3);
+    }
+    red[pq][r] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < NB) publish(sol + (size_t)u.blk * NB + tid, (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]));
+  } else {
+    // x[c] = sum_r W[r, c] v[r]
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = pr + 16 * i;
+      const double2 w0 = *reinterpret_cast<const double2*>(Ws + ((size_t)q * NB + rr) * 4);
+      const double2 w1 = *reinterpret_cast<const double2*>(Ws + ((size_t)q * NB + rr) * 4 + 2);
+      const double v = vs[rr];
+      s0 = fma(w0.x, v, s0); s1 = fma(w0.y, v, s1); s2 = fma(w1.x, v, s2); s3 = fma(w1.y, v, s3);
+    }
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if (pr == 0) {
+      double* o4 = sol + (size_t)u.blk * NB + 4 * q;
+      publish(o4, s0); publish(o4 + 1, s1); publish(o4 + 2, s2); publish(o4 + 3, s3);
+    }
   }
 }
 
+std::atomic<unsigned long long> g_sweep_attr[2];
 std::atomic<unsigned long long> g_potrf_attr{0};
 }  // namespace
 
@@ -635,6 +732,43 @@ int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info) {
   CIP_CUDA(cudaStreamCreateWithPriority(&p->sc, cudaStreamNonBlocking, hi));
   for (auto* e : {&p->evT[0], &p->evT[1], &p->evR[0], &p->evR[1], &p->evS})
     CIP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  // ---- work units of the persistent triangular sweeps (see trsv_sweep_kernel)
+  {
+    const int np = p->npanels;
+    const int seg = std::min(32, std::max(8, (np + 3) / 4));
+    p->maxseg = std::max(1, (np - 1 + seg - 1) / seg);
+    std::vector<SweepUnit> uf, ub;
+    struct Keyed { int key, fin, blk; SweepUnit u; };
+    for (int dir = 0; dir < 2; ++dir) {
+      std::vector<Keyed> v;
+      for (int t = 0; t < np; ++t) {                 // t = position of the block row in sweep order
+        const int nseg = std::max(1, (t + seg - 1) / seg);
+        for (int sg = 0; sg < nseg; ++sg) {
+          const int t0 = sg * seg, t1 = std::min(t, (sg + 1) * seg);      // dependencies [t0, t1) in sweep order
+          SweepUnit u;
+          u.blk = dir == 0 ? t : np - 1 - t;
+          u.d0 = dir == 0 ? t0 : np - 1 - t0;
+          u.nd = t1 - t0;
+          u.seg = sg; u.nseg = nseg; u.fin = (sg == nseg - 1);
+          v.push_back(Keyed{t1 - 1, u.fin, t, u});   // ordered by the last solution block the unit waits for
+        }
+      }
+      std::stable_sort(v.begin(), v.end(), [](const Keyed& a, const Keyed& b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.fin != b.fin) return a.fin > b.fin;
+        return a.blk < b.blk;
+      });
+      for (auto& k : v) (dir == 0 ? uf : ub).push_back(k.u);
+    }
+    p->nunits = (int)uf.size();
+    CIP_CUDA(cudaMalloc(&p->units_fwd, sizeof(SweepUnit) * uf.size()));
+    CIP_CUDA(cudaMalloc(&p->units_bwd, sizeof(SweepUnit) * ub.size()));
+    CIP_CUDA(cudaMemcpy(p->units_fwd, uf.data(), sizeof(SweepUnit) * uf.size(), cudaMemcpyHostToDevice));
+    CIP_CUDA(cudaMemcpy(p->units_bwd, ub.data(), sizeof(SweepUnit) * ub.size(), cudaMemcpyHostToDevice));
+    CIP_CUDA(cudaMalloc(&p->sweep_part, sizeof(double) * (size_t)np * p->maxseg * NB));
+    CIP_CUDA(cudaMalloc(&p->sweep_err, sizeof(int)));
+    CIP_CUDA(cudaMemset(p->sweep_err, 0, sizeof(int)));
+  }
   return 0;
 }
 
@@ -643,6 +777,9 @@ void chol_free_plan(CholPlan* p) {
   for (auto e : {p->evT[0], p->evT[1], p->evR[0], p->evR[1], p->evS})
     if (e) cudaEventDestroy(e);
   p->sc = nullptr;
+  for (void* q : {(void*)p->units_fwd, (void*)p->units_bwd, (void*)p->sweep_part, (void*)p->sweep_err})
+    if (q) cudaFree(q);
+  p->units_fwd = p->units_bwd = nullptr; p->sweep_part = nullptr; p->sweep_err = nullptr;
 }
 
 // Two-level blocked right-looking Cholesky with look-ahead.
@@ -811,20 +948,24 @@ int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
   return 0;
 }
 
-int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s) {
-  for (int jb = 0; jb < p.npanels; ++jb) {
-    trsv_fwd_kernel<<<p.npanels - jb, 512, 0, s>>>(p.H, p.ld, p.Winv, jb, b, y);
-    CIP_CHECK_LAUNCH();
-  }
+namespace {
+template <bool FWD>
+int run_sweep(const CholPlan& p, const double* rhs, double* sol, cudaStream_t s) {
+  CIP_TRY(ensure_dyn_smem((const void*)trsv_sweep_kernel<FWD>, SWEEP_SMEM, &g_sweep_attr[FWD ? 0 : 1]));
+  // preset the hand-off buffers to the sentinel (all-ones bytes)
+  CIP_CUDA(cudaMemsetAsync(sol, 0xFF, sizeof(double) * (size_t)p.npanels * NB, s));
+  CIP_CUDA(cudaMemsetAsync(p.sweep_part, 0xFF, sizeof(double) * (size_t)p.npanels * p.maxseg * NB, s));
+  trsv_sweep_kernel<FWD><<<p.nunits, SWEEP_THREADS, SWEEP_SMEM, s>>>(
+      p.H, p.ld, p.Winv, reinterpret_cast<const SweepUnit*>(FWD ? p.units_fwd : p.units_bwd), rhs, sol, p.sweep_part,
+      p.maxseg, p.sweep_err);
+  CIP_CHECK_LAUNCH();
   return 0;
 }
+}  // namespace
 
-int chol_bwd(const CholPlan& p, double* y, double* x, cudaStream_t s) {
-  for (int jb = p.npanels - 1; jb >= 0; --jb) {
-    trsv_bwd_kernel<<<jb + 1, 512, 0, s>>>(p.H, p.ld, p.Winv, jb, y, x);
-    CIP_CHECK_LAUNCH();
-  }
-  return 0;
-}
+// y receives the solution of L y = b (b is read only; the two must not alias)
+int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s) { return run_sweep<true>(p, b, y, s); }
+// x receives the solution of L' x = y
+int chol_bwd(const CholPlan& p, double* y, double* x, cudaStream_t s) { return run_sweep<false>(p, y, x, s); }
 
 }  // namespace cip

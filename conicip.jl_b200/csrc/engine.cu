@@ -196,6 +196,63 @@ int set_scaling_from_user(cip_engine* h, const int* kind, const double* fa, cons
   return 0;
 }
 
+// Row-sharded form of H: the partial Gram matrix is produced tile-major in a few ranges of the (reversed) tile
+// order; each range is all-reduced (NCCL, stream cs) and unpacked into H4 while the next ranges are still being
+// computed, so only the last, small range (the tip of the triangle) is exposed.  Ranges alternate between two
+// streams: consecutive SYRK launches do not serialise on each other's last wave.
+int form_H_sharded(cip_engine* h, const double* cin, int k_rows) {
+  const NcclApi* api = nccl_api();
+  if (!api) return -1;
+  cudaStream_t s = h->stream;
+  const int T = h->n_pad / TILE;
+  const long long ntiles = (long long)T * (T + 1) / 2;
+  const int nsm = sm_count();
+  // range ends as fractions of the tiles, rounded to whole waves; small problems: one range
+  const double frac[6] = {0.40, 0.70, 0.85, 0.93, 0.97, 1.0};
+  long long ends[6];
+  int nr = 0;
+  long long prev = 0;
+  for (int i = 0; i < 6; ++i) {
+    long long e = (i == 5) ? ntiles : (long long)(frac[i] * ntiles) / nsm * nsm;
+    if (e <= prev) continue;
+    if (ntiles < 4LL * nsm) e = ntiles;
+    ends[nr++] = e;
+    prev = e;
+    if (e == ntiles) break;
+  }
+  CIP_CUDA(cudaEventRecord(h->evc[15], s));                 // Atil ready
+  CIP_CUDA(cudaStreamWaitEvent(h->s2, h->evc[15], 0));
+  long long t0 = 0;
+  for (int i = 0; i < nr; ++i) {
+    cudaStream_t st = (i & 1) ? h->s2 : s;
+    GemmArgs a{};
+    a.lower = 1; a.ntm = a.ntn = T; a.sym = 1; a.reverse = 1;
+    a.nk = k_rows / 32;
+    a.Cin = cin; a.Cout = h->H4; a.Ctm = h->Hp; a.ldc = h->n_pad; a.alpha = 1.0;
+    a.tile_begin = (int)t0; a.tile_count = (int)(ends[i] - t0);
+    if (i == nr - 1) { a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES; }     // split-K only for the very last wave
+    CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, st));
+    CIP_CUDA(cudaEventRecord(h->evc[i], st));
+    CIP_CUDA(cudaStreamWaitEvent(h->cs, h->evc[i], 0));
+    double* seg = h->Hp + (size_t)t0 * TILE * TILE;
+    const int r = api->AllReduce(seg, seg, (size_t)a.tile_count * TILE * TILE, kNcclFloat64, kNcclSum, h->comm, h->cs);
+    if (r != 0) {
+      set_error("ncclAllReduce failed: %s", api->GetErrorString(r));
+      return -1;
+    }
+    CIP_TRY(unpack_tile_major(a, h->cs));
+    t0 = ends[i];
+  }
+  if (nr > 1) {
+    CIP_CUDA(cudaEventRecord(h->evc[14], h->s2));
+    CIP_CUDA(cudaStreamWaitEvent(s, h->evc[14], 0));
+  }
+  CIP_CUDA(cudaEventRecord(h->ev[2], s));                   // every SYRK range done; what follows is the exposed wait
+  CIP_CUDA(cudaEventRecord(h->evc[13], h->cs));
+  CIP_CUDA(cudaStreamWaitEvent(s, h->evc[13], 0));
+  return 0;
+}
+
 int form_H(cip_engine* h) {
   if (!h->have_scaling) {
     set_error("no scaling set (call cip_factor / cip_set_scaling / cip_nt_scaling first)");
@@ -208,6 +265,13 @@ int form_H(cip_engine* h) {
   const double* cin = (h->rank == 0) ? h->Qq4 : nullptr;
   // rows of Atil beyond m_pad hold sqrt(rho)*G (constant): H' = Q + Atil'Atil + rho G'G, added on rank 0 only
   const int k_rows = h->m_pad + ((h->rank == 0) ? h->aug_rows : 0);
+  if (h->comm && h->Hp) {
+    CIP_TRY(form_H_sharded(h, cin, k_rows));
+    if (h->opt.reg_delta != 0.0) CIP_TRY(add_diag_q4(h->H4, h->n_pad, 0, h->n, h->opt.reg_delta, 0, s));
+    CIP_CUDA(cudaEventRecord(h->ev[3], s));
+    h->st.syrk_flops = (double)h->m * (double)h->n * (double)h->n;
+    return 0;
+  }
   if (k_rows > 0) {
     GemmArgs a{};
     a.lower = 1; a.ntm = a.ntn = h->n_pad / TILE; a.sym = 1;
@@ -302,6 +366,23 @@ int factor_H(cip_engine* h) {
 
 namespace cip {
 int engine_allreduce(cip_engine* h, double* buf, size_t count) { return allreduce(h, buf, count); }
+int engine_setup_comm(cip_engine* h) {
+  if (!h->comm || h->Hp) return 0;
+  if (const char* env = getenv("CIP_OVERLAP_REDUCE")) if (atoi(env) == 0) return 0;   // A/B switch: plain all-reduce of H4
+  CIP_CUDA(cudaSetDevice(h->device));
+  const int T = h->n_pad / TILE;
+  if (h->m_pad + h->aug_rows == 0) {
+    // (a shard without rows still takes part: its tiles are Q or zero) -- the operand map must exist
+    CIP_TRY(make_q4_tensor_map(&h->mapAtil.map, h->Atil4, h->n_pad, 8));
+  }
+  CIP_TRY(dev_alloc(h, &h->Hp, (size_t)T * (T + 1) / 2 * TILE * TILE, false));
+  int lo = 0, hi = 0;
+  CIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CIP_CUDA(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, hi));
+  CIP_CUDA(cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking));
+  for (auto& e : h->evc) CIP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return 0;
+}
 const char* last_error_string() { return g_err; }
 }  // namespace cip
 
@@ -677,6 +758,10 @@ int cip_destroy(cip_handle h) {
   for (auto v : h->pv) if (v) cudaFree(v);
   chol_free_plan(&h->cholH);
   chol_free_plan(&h->cholS);
+  if (h->Hp) cudaFree(h->Hp);
+  if (h->cs) cudaStreamDestroy(h->cs);
+  if (h->s2) cudaStreamDestroy(h->s2);
+  for (auto e : h->evc) if (e) cudaEventDestroy(e);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   cudaGetLastError();
@@ -713,7 +798,7 @@ int cip_comm_init(cip_handle h, int nranks, int rank, const unsigned char id[128
   }
   h->nranks = nranks;
   h->rank = rank;
-  return 0;
+  return engine_setup_comm(h);
 }
 
 int cip_set_scaling(cip_handle h, const int* kind, const double* fa, const double* fb, const double* fD,
@@ -890,6 +975,34 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   CIP_TRY(stage_out(h, dy, h->nv[5], h->n));
   if (h->p) CIP_TRY(stage_out(h, dw, h->pv[4], h->p));
   CIP_TRY(stage_out(h, dv, h->mv[5], h->m));
+  h->st.solves++;
+  if (h->need_sync || h->always_sync) {
+    // the call synchronises anyway: also read the give-up flag of the persistent sweeps (a hand-off that never
+    // arrived -- a bug, not a numerical condition -- must not pass for a solution)
+    int bad[2] = {0, 0};
+    CIP_CUDA(cudaMemcpyAsync(&bad[0], h->cholH.sweep_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (h->p) CIP_CUDA(cudaMemcpyAsync(&bad[1], h->cholS.sweep_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CIP_TRY(finish(h));
+    if (bad[0] || bad[1]) {
+      set_error("cip_solve: a triangular sweep gave up waiting for a solution block (internal error)");
+      return -4;
+    }
+    return 0;
+  }
+  return finish(h);
+}
+
+int cip_solve_H(cip_handle h, const double* rhs, double* x) {
+  CIP_TRY(check(h));
+  if (h->multi) { set_error("cip_solve_H: test hook, single-device handles only"); return -1; }
+  if (!h->have_factor) { set_error("cip_solve_H before cip_factor"); return -1; }
+  cudaStream_t s = h->stream;
+  CIP_TRY(stage_in(h, h->nv[2], rhs, h->n));
+  CIP_CUDA(cudaEventRecord(h->ev[6], s));
+  CIP_TRY(chol_fwd(h->cholH, h->nv[2], h->nv[3], s));
+  CIP_TRY(chol_bwd(h->cholH, h->nv[3], h->nv[5], s));
+  CIP_CUDA(cudaEventRecord(h->ev[7], s));
+  CIP_TRY(stage_out(h, x, h->nv[5], h->n));
   h->st.solves++;
   return finish(h);
 }

@@ -51,6 +51,11 @@ struct cip_engine {
   // NCCL
   void* comm = nullptr;
   int nranks = 1, rank = 0;
+  // overlapped Gram reduction (row-sharded handles): tile-major partial Gram matrix, all-reduced range by range
+  // on `cs` while the SYRK of the later ranges still runs (alternating between the handle's stream and `s2`)
+  double* Hp = nullptr;
+  cudaStream_t cs = nullptr, s2 = nullptr;
+  cudaEvent_t evc[16] = {};
   // stats
   cip_stats_t st{};
   cudaEvent_t ev[8] = {};
@@ -67,6 +72,8 @@ int engine_create_single(cip_handle* out, int n, int m, int p, const double* Q, 
                          const double* G, int ldg, const cip_csc* Qs, const cip_csc* As, const cip_csc* Gs,
                          int ncones, const int* cone_type, const int* cone_dim, const cip_options* opts);
 const char* last_error_string();
+// buffers / streams of the overlapped Gram reduction, once the communicator exists (engine.cu)
+int engine_setup_comm(cip_engine* h);
 
 // ---- single-process multi-GPU front (multi.cu): same contracts as the C ABI entry points, global vectors
 int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq, const double* A, int lda,

@@ -27,6 +27,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
 
 __device__ __forceinline__ void tile_of(const GemmArgs& a, int t, int& ti, int& tj) {
   if (a.lower) {
+    if (a.reverse) t = a.ntm * (a.ntm + 1) / 2 - 1 - t;
     // Band rasterisation of the lower-triangular tile grid: bands of BAND tile rows, column-major
     // inside a band, so the ~148 concurrently resident CTAs cover ~BAND rows x ~148/BAND columns and
     // share their X / Y panels in L2 (instead of one long row of tiles with 148 distinct Y panels).
@@ -65,7 +66,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   int ti, tj;
   // CTAs below tail0 own a whole tile; above it, ksplit consecutive CTAs share one (k tiles [kt0, kt1))
   const bool split = (int)blockIdx.x >= a.tail0 && a.ksplit > 1;
-  const int tile = split ? a.tail0 + ((int)blockIdx.x - a.tail0) / a.ksplit : (int)blockIdx.x;
+  const int tile = a.tile_begin + (split ? a.tail0 + ((int)blockIdx.x - a.tail0) / a.ksplit : (int)blockIdx.x);
   const int sp = split ? ((int)blockIdx.x - a.tail0) % a.ksplit : 0;
   tile_of(a, tile, ti, tj);
   const int kt0 = split ? sp * a.kchunk : 0;
@@ -85,7 +86,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (warp == CONSUMER_WARPS) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && kt1 > kt0) {
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmY);
       const int xr = (a.x_row0 + ti * BM) * 4;
@@ -159,6 +160,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
   const int row_base = a.c_row0 + ti * BM + warp_m * 64 + g;
   const int col_base = a.c_col0 + tj * BN + warp_n * 32 + 2 * t;
+  double* tm = a.Ctm ? a.Ctm + (size_t)tile * (size_t)(BM * BN) : nullptr;
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int col = col_base + ni * 8;
@@ -170,7 +172,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       if (a.Cin) v = *reinterpret_cast<const double2*>(a.Cin + idx);
       v.x += alpha * acc[mi][ni][0];
       v.y += alpha * acc[mi][ni][1];
-      *reinterpret_cast<double2*>(a.Cout + idx) = v;
+      if (tm) *reinterpret_cast<double2*>(tm + q4_index(warp_m * 64 + g + mi * 8, warp_n * 32 + 2 * t + ni * 8, BM)) = v;
+      else *reinterpret_cast<double2*>(a.Cout + idx) = v;
     }
   }
 }
@@ -178,7 +181,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // C tile = Cin tile + sum over splits (in split order) of the partial tiles in the workspace
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs a) {
   int ti, tj;
-  tile_of(a, a.tail0 + blockIdx.x, ti, tj);
+  const int tile = a.tile_begin + a.tail0 + blockIdx.x;
+  tile_of(a, tile, ti, tj);
+  double* tm = a.Ctm ? a.Ctm + (size_t)tile * (size_t)(BM * BN) : nullptr;
   const size_t slab = (size_t)(BM * BN);
   const double* wt = a.ws + (size_t)blockIdx.x * a.ksplit * slab;
   for (int e = threadIdx.x * 2; e < BM * BN; e += 512) {
@@ -195,7 +200,21 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmArgs a) {
       v.x += ci.x;
       v.y += ci.y;
     }
-    *reinterpret_cast<double2*>(a.Cout + idx) = v;
+    if (tm) *reinterpret_cast<double2*>(tm + e) = v;             // the workspace tiles are tile-local Q4 already
+    else *reinterpret_cast<double2*>(a.Cout + idx) = v;
+  }
+}
+
+// Cout tile <- tile-major tile (both Q4: 512-double runs move as they are)
+__global__ void __launch_bounds__(256) unpack_tiles_kernel(const GemmArgs a) {
+  int ti, tj;
+  const int tile = a.tile_begin + blockIdx.x;
+  tile_of(a, tile, ti, tj);
+  const double* tm = a.Ctm + (size_t)tile * (size_t)(BM * BN);
+  for (int e = threadIdx.x * 2; e < BM * BN; e += 512) {
+    const int quad = e / (BM * 4), lr = (e % (BM * 4)) >> 2, c = e & 3;
+    const size_t idx = q4_index(a.c_row0 + ti * BM + lr, a.c_col0 + tj * BN + quad * 4 + c, a.ldc);
+    *reinterpret_cast<double2*>(a.Cout + idx) = *reinterpret_cast<const double2*>(tm + e);
   }
 }
 
@@ -236,11 +255,21 @@ int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long k
   return 0;
 }
 
+int unpack_tile_major(const GemmArgs& a, cudaStream_t stream) {
+  const long long all_tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
+  const long long tiles = a.tile_count > 0 ? a.tile_count : all_tiles - a.tile_begin;
+  if (tiles <= 0) return 0;
+  unpack_tiles_kernel<<<(unsigned)tiles, 256, 0, stream>>>(a);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a, cudaStream_t stream) {
   CIP_TRY(ensure_dyn_smem((const void*)gemm_nt_kernel, SMEM_BYTES, &g_attr_set));
   const int nsm = sm_count();      // one CTA per SM (192 KB of shared memory each): a wave is nsm tiles
-  const long long tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
-  if (tiles <= 0 || a.nk <= 0) return 0;
+  const long long all_tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
+  const long long tiles = a.tile_count > 0 ? a.tile_count : all_tiles - a.tile_begin;
+  if (tiles <= 0 || (a.nk <= 0 && !a.Ctm)) return 0;      // (nk = 0 with tile-major output: the tiles are Cin, or zero)
   GemmArgs b = a;
   b.ksplit = 1;
   b.kchunk = a.nk;

@@ -39,6 +39,13 @@ struct GemmArgs {
   long long ws_doubles;
   int tail0;           // filled in by launch_gemm_nt: first split tile (CTAs below it contract all of K)
   int ksplit, kchunk;  //   number of splits of a tail tile, k tiles per split
+  // Tile-major output in ranges (row-sharded SYRK: the partial Gram matrix is all-reduced range by range while
+  // later ranges are still being computed).  The launch covers the linear tile indices [tile_begin, tile_begin +
+  // tile_count) (tile_count = 0: all); with `Ctm` set, tile t is written to Ctm + t * 128*128 in tile-local Q4
+  // (ld = 128) instead of Cout; `reverse` walks the triangular grid backwards (big row bands first), so that
+  // the last range, whose all-reduce cannot hide behind compute, is the small tip of the triangle.
+  int tile_begin, tile_count, reverse;
+  double* Ctm;
 };
 constexpr long long GEMM_WS_DOUBLES = 2048ll * 128 * 128;   // 2048 partial tiles (268 MB)
 
@@ -47,6 +54,9 @@ int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long k
 
 // Launch on `stream`.
 int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a, cudaStream_t stream);
+
+// Cout (Q4, ldc) <- the tile-major tiles [tile_begin, tile_begin + tile_count) of Ctm (same grid description as the launch)
+int unpack_tile_major(const GemmArgs& a, cudaStream_t stream);
 
 int gemm_nt_smem_bytes();
 

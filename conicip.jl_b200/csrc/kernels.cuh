@@ -101,6 +101,11 @@ struct CholPlan {
   // while the bulk trailing update of the previous panel runs on the caller's stream
   cudaStream_t sc = nullptr;
   cudaEvent_t evT[2] = {}, evR[2] = {}, evS = nullptr;
+  // persistent triangular sweeps: work units (device), partial sums of split block rows, error flag
+  void *units_fwd = nullptr, *units_bwd = nullptr;
+  int nunits = 0, maxseg = 1;
+  double* sweep_part = nullptr;
+  int* sweep_err = nullptr;
 };
 int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info);
 void chol_free_plan(CholPlan* p);
@@ -113,9 +118,9 @@ struct CholDist {
   void* comm = nullptr;   // ncclComm_t
 };
 int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d);
-// b (length n_pad) is overwritten with work; y receives the solution of L y = b
+// y receives the solution of L y = b (b is read only; b and y must not alias; both of length n_pad)
 int chol_fwd(const CholPlan& p, double* b, double* y, cudaStream_t s);
-// y is overwritten with work; x receives the solution of L' x = y
+// x receives the solution of L' x = y
 int chol_bwd(const CholPlan& p, double* y, double* x, cudaStream_t s);
 
 // small vector helpers (vecops.cu)

@@ -311,6 +311,8 @@ int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq,
       return -1;
     }
     for (int q = 0; q < N; ++q) { M->shard[q]->comm = comms[q]; M->shard[q]->nranks = N; M->shard[q]->rank = q; }
+    rc = M->run([&](int q) { return engine_setup_comm(M->shard[q]); });
+    if (rc != 0) { multi_destroy(h); return rc; }
   }
   h->device = M->dev[0];
   *out = h;

@@ -275,6 +275,13 @@ class Engine:
                               self._ptr(dw, self.p) if self.p else None, self._ptr(dv, self.m)))
         return dy, dw, dv
 
+    def solve_H(self, rhs):
+        """x = inv(H) rhs through the two triangular sweeps alone (`cip_solve_H`, test / bench hook)."""
+        dev, (rhs,) = self._prep(rhs)
+        x = self._new(dev, self.n)
+        check(lib().cip_solve_H(self._h, self._ptr(rhs, self.n), self._ptr(x, self.n)))
+        return x
+
     # ------------------------------------------------------------------ cone kernels
     def nt_scaling(self, v, s):
         dev, (v, s) = self._prep(v, s)

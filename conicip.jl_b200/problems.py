@@ -180,3 +180,55 @@ def config4_device(n=16384, m=262144, seed=4, rank=0, nranks=1, scale_rows=None)
     s0_full = 0.1 + torch.rand(m, generator=gs, dtype=torch.float64, device="cuda")
     b = At.t() @ y0 - s0_full[r0:r0 + m_loc]
     return dict(name="C4", At=At, b=b, qdiag=qdiag, Q=Q, c=c, cone_dims=[("R", m_loc)], n=n, m=m, m_loc=m_loc)
+
+
+def _svec(Z):
+    """vecm of src/ConicIP.jl:128-151 (row-major upper triangle, off-diagonals * sqrt 2)."""
+    k = Z.shape[0]
+    iu = np.triu_indices(k)
+    x = Z[iu].copy()
+    x[iu[0] != iu[1]] *= np.sqrt(2.0)
+    return x
+
+
+def _smat(x):
+    """mat of src/ConicIP.jl:93-119."""
+    k = int(round((np.sqrt(1 + 8 * len(x)) - 1) / 2))
+    Z = np.zeros((k, k))
+    iu = np.triu_indices(k)
+    Z[iu] = x
+    off = iu[0] != iu[1]
+    Z[iu[0][off], iu[1][off]] /= np.sqrt(2.0)
+    return Z + np.triu(Z, 1).T
+
+
+def config5(n=20000, k=64, p=1000, seed=5):
+    """C5 -- the MOI-shaped LP (Q = 0): x >= 0 on all n variables, one PSD block of order k on the first
+    k(k+1)/2 variables, p sparse equality rows (~10 nnz/row); strictly feasible primal and dual by
+    construction, so it is bounded.  n = 20000, k = 64, p = 1000 is BASELINE.json's config 5."""
+    rng = np.random.default_rng(seed)
+    dim = k * (k + 1) // 2
+    m = n + dim
+    A = np.zeros((m, n))
+    A[np.arange(n), np.arange(n)] = 1.0
+    A[n + np.arange(dim), np.arange(dim)] = 1.0
+    B = rng.standard_normal((k, k)) / np.sqrt(k)
+    X0 = B @ B.T + 0.5 * np.eye(k)
+    y0 = rng.uniform(0.5, 1.5, n)
+    y0[:dim] = np.abs(_svec(X0)) + 0.05            # > 0 entrywise ...
+    Xs = _smat(y0[:dim])
+    Xs += (0.1 - min(0.0, np.linalg.eigvalsh(Xs).min())) * np.eye(k)      # ... and mat() positive definite
+    y0[:dim] = _svec(Xs)
+    assert np.linalg.eigvalsh(_smat(y0[:dim])).min() > 0 and y0.min() > 0
+    b = np.zeros(m)
+    G = np.zeros((p, n))
+    for i in range(p):
+        G[i, rng.choice(n, min(10, n), replace=False)] = rng.standard_normal(min(10, n))
+    d = G @ y0
+    v0 = np.zeros(m)
+    v0[:n] = rng.uniform(0.5, 1.5, n)
+    Bz = rng.standard_normal((k, k)) / np.sqrt(k)
+    v0[n:] = _svec(Bz @ Bz.T + 0.5 * np.eye(k))
+    w0 = rng.standard_normal(p)
+    c = G.T @ w0 - A.T @ v0                          # stationarity (src/ConicIP.jl:747,753): Qy + G'w - A'v = c
+    return _prob("C5", np.zeros((n, n)), c, A, b, [("R", n), ("S", dim)], G, d, optTol=1e-8)

@@ -214,6 +214,9 @@ int cip_get_H(cip_handle h, double* out, int ldo);
 /* form H = Q + (F^-T A)'(F^-T A) only (no factorisation) -- test/bench hook */
 int cip_form_H(cip_handle h);
 int cip_factor_H(cip_handle h);
+/* x = inv(H) rhs with the current Cholesky factor: the two triangular sweeps of LEVEL 3 alone
+ * (src/kktsolvers.jl:299 without the pivot algebra around it) -- test/bench hook; n-vectors */
+int cip_solve_H(cip_handle h, const double* rhs, double* x);
 int cip_sync(cip_handle h);
 /* The handle launches everything on one CUDA stream (its own by default).  cip_set_stream
  * makes it use the caller's stream instead (e.g. PyTorch's current stream; the value 0 is the

@@ -118,3 +118,62 @@ def test_c4_headline_size_properties():
     dy2, _, dv2 = eng.solve(2.0 * ry, None, 2.0 * rv)
     assert torch.equal(dy2, 2.0 * dy) and torch.equal(dv2, 2.0 * dv)
     eng.close()
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_c2_kkt_unit_matches_oracle(c2):
+    """BASELINE config 2 at full size against the oracle itself: one KKT unit (NT scaling, H = Q + Atil'Atil,
+    Cholesky, the pivot solve) through `O.kktsolver_chol` on the host and through the engine, same inputs."""
+    import oracle as O
+    prob, eng = c2
+    Q, A = prob["Q"], prob["A"]
+    m, n = A.shape
+    rng = np.random.default_rng(42)
+    v, s = rng.uniform(0.05, 20.0, m), rng.uniform(0.05, 20.0, m)
+    ry, rv = rng.standard_normal(n), rng.standard_normal(m)
+    lam = eng.factor_from_point(v, s)
+    dy, _, dv = eng.solve(ry, None, rv)
+    F = O.Block([O.Diag(np.sqrt(s / v))])                                  # nt_scaling, src/ConicIP.jl:598
+    solve = O.kktsolver_chol(Q, A, np.zeros((0, n)), prob["cone_dims"])(F, F.inv_adjoint())
+    oy, _, ov = solve(ry, np.zeros(0), rv)
+    assert _rel(lam, F.mul(v)) < 1e-14
+    assert _rel(dy, oy) < 1e-9 and _rel(dv, ov) < 1e-9, (_rel(dy, oy), _rel(dv, ov))
+
+
+def test_c3_full_size_solve_matches_oracle():
+    """BASELINE config 3 at full size (n=4096, 512 Q cones of dim 33, p=256): the whole solve to 1e-8 on the
+    device against the oracle's: same status, iteration count within 1, y / v / w to 1e-6 relative (the
+    north_star tolerances), residuals below 1e-8."""
+    import conicip_b200 as cb
+    import oracle as O
+    prob = P.config3()
+    so = O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"],
+                   optTol=1e-8, kktsolver=O.kktsolver_chol)
+    s = cb.conicIP_native(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"],
+                          optTol=1e-8)
+    assert s.status == so.status == "Optimal"
+    assert abs(s.Iter - so.Iter) <= 1, (s.Iter, so.Iter)
+    assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8
+    assert _rel(s.y, so.y) < 1e-6 and _rel(s.v, so.v) < 1e-6 and _rel(s.w, so.w) < 1e-6, \
+        (_rel(s.y, so.y), _rel(s.v, so.v), _rel(s.w, so.w))
+
+
+def test_c5_shaped_lp_with_s64_block_matches_oracle():
+    """BASELINE config 5's shape (LP, x >= 0, ONE S block of order 64 = 2080 rows, sparse equality rows) with n
+    small enough for the oracle: status, iterations within 1 and the solution against `O.kktsolver_qr`, the
+    only reference solver that is right for S cones."""
+    import conicip_b200 as cb
+    import oracle as O
+    prob = P.config5(n=2200, k=64, p=60)
+    so = O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"],
+                   optTol=1e-8, kktsolver=O.kktsolver_qr)
+    s = cb.conicIP_native(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"],
+                          optTol=1e-8)
+    assert s.status == so.status == "Optimal", (s.status, so.status)
+    assert abs(s.Iter - so.Iter) <= 1, (s.Iter, so.Iter)
+    assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8
+    assert _rel(s.y, so.y) < 1e-6 and _rel(s.v, so.v) < 1e-5, (_rel(s.y, so.y), _rel(s.v, so.v))
+    assert abs(s.pobj - so.pobj) <= 1e-7 * (1 + abs(so.pobj))

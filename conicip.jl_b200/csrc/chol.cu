@@ -730,7 +730,10 @@ int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info) {
   int lo = 0, hi = 0;
   CIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CIP_CUDA(cudaStreamCreateWithPriority(&p->sc, cudaStreamNonBlocking, hi));
-  for (auto* e : {&p->evT[0], &p->evT[1], &p->evR[0], &p->evR[1], &p->evS})
+  CIP_CUDA(cudaStreamCreateWithPriority(&p->sd, cudaStreamNonBlocking, hi));
+  CIP_CUDA(cudaStreamCreateWithPriority(&p->se, cudaStreamNonBlocking, hi));
+  CIP_CUDA(cudaStreamCreateWithPriority(&p->sb, cudaStreamNonBlocking, hi));
+  for (auto* e : {&p->evT[0], &p->evT[1], &p->evR[0], &p->evR[1], &p->evS, &p->evD[0], &p->evD[1], &p->evP, &p->evE})
     CIP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   // ---- work units of the persistent triangular sweeps (see trsv_sweep_kernel)
   {
@@ -774,72 +777,167 @@ int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info) {
 
 void chol_free_plan(CholPlan* p) {
   if (p->sc) cudaStreamDestroy(p->sc);
-  for (auto e : {p->evT[0], p->evT[1], p->evR[0], p->evR[1], p->evS})
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  p->graph_exec = nullptr;
+  if (p->sd) cudaStreamDestroy(p->sd);
+  if (p->se) cudaStreamDestroy(p->se);
+  if (p->sb) cudaStreamDestroy(p->sb);
+  for (auto e : {p->evT[0], p->evT[1], p->evR[0], p->evR[1], p->evS, p->evD[0], p->evD[1], p->evP, p->evE})
     if (e) cudaEventDestroy(e);
-  p->sc = nullptr;
+  p->sc = nullptr; p->sd = nullptr; p->se = nullptr; p->sb = nullptr;
   for (void* q : {(void*)p->units_fwd, (void*)p->units_bwd, (void*)p->sweep_part, (void*)p->sweep_err})
     if (q) cudaFree(q);
   p->units_fwd = p->units_bwd = nullptr; p->sweep_part = nullptr; p->sweep_err = nullptr;
 }
 
-// Two-level blocked right-looking Cholesky with look-ahead.
-//   outer panel = OUTER inner panels (512 columns).  Inside an outer panel every 128-wide inner
-//   panel is factored (potrf_diag), solved against all rows below (TRSM as a GEMM with inv(L11))
-//   and applied only to the remaining columns of the outer panel.  The trailing matrix then gets
-//   ONE update with K = 512, which amortises the C-tile read/write and the pipeline fill that
-//   dominate K = 128 tiles.  The block column of the next outer panel is updated first on the
-//   high-priority stream `sc`, so its factorisation overlaps the bulk update running on `s`.
-int chol_factor(const CholPlan& p, cudaStream_t s) {
-  constexpr int OUTER = 4;
-  const int smem = POTRF_SMEM;
-  CIP_TRY(ensure_dyn_smem((const void*)potrf_diag_kernel, smem, &g_potrf_attr));
-  cudaStream_t sc = p.sc;
+namespace {
+// Whether the next outer panel's block column is fed inner panel by inner panel (four K = 128 updates beside the
+// chain) or gets one K = 512 update after the outer panel is complete.  Feeding shortens the panel chain but
+// does the same flops on less efficient tiles; it pays when the factorisation is chain-bound (small n, or the
+// trailing matrix shared by several ranks).  Both Cholesky variants take the same decision from the same
+// inputs, so single-GPU and distributed factors stay bit-identical.
+bool feed_next_panel(int npanels, int nranks) {
+  if (const char* env = getenv("CIP_CHOL_PIPE")) return atoi(env) != 0;
+  return npanels <= 64 || nranks >= 4;
+}
+
+// Factorisation of the outer panel [J0, J1) of 128-column panels on the chain stream sc.  Per inner panel:
+// potrf_diag (L11 and its inverse), L21 = A21 inv(L11)' for all rows below, then the update of the NEXT inner
+// panel's column only -- that is all the next potrf waits for.  The update of the remaining columns of the outer
+// panel runs beside the chain on p.sd (inner look-ahead).  `hook(jb)` is called as soon as column jb is final
+// (p.evP has just been recorded on sc behind it): the callers feed the next outer panel / the other ranks from it.
+template <typename Hook>
+int factor_outer_panel(const CholPlan& p, int J0, int J1, cudaStream_t sc, int smem, Hook hook) {
   const int np = p.npanels;
-  CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));
-  CIP_CUDA(cudaEventRecord(p.evS, s));
-  CIP_CUDA(cudaStreamWaitEvent(sc, p.evS, 0));
-  int outer = 0;
-  for (int J0 = 0; J0 < np; J0 += OUTER, ++outer) {
-    const int J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
-    for (int jb = J0; jb < J1; ++jb) {
-      const int j0 = jb * NB;
-      potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
-      CIP_CHECK_LAUNCH();
-      const int rem = np - jb - 1;
-      if (rem == 0) break;
+  for (int jb = J0; jb < J1; ++jb) {
+    const int j0 = jb * NB;
+    potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
+    CIP_CHECK_LAUNCH();
+    const int rem = np - jb - 1;
+    if (rem > 0) {
       GemmArgs t{};   // L21 = A21 * inv(L11)'
       t.lower = 0; t.ntm = rem; t.ntn = 1; t.sym = 0;
       t.x_row0 = j0 + NB; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = NB / 32;
       t.Cin = nullptr; t.Cout = p.H; t.ldc = p.ld; t.c_row0 = j0 + NB; t.c_col0 = j0; t.alpha = 1.0;
       CIP_TRY(launch_gemm_nt(p.mapH, p.mapWinv, t, sc));
-      const int inner_cols = J1 - jb - 1;
-      if (inner_cols > 0) {   // update the rest of this outer panel's columns (K = 128)
-        GemmArgs c{};
-        c.lower = 0; c.ntm = rem; c.ntn = inner_cols; c.sym = 0;
-        c.x_row0 = j0 + NB; c.y_row0 = j0 + NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
-        c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + NB; c.c_col0 = j0 + NB; c.alpha = -1.0;
-        CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
+    }
+    CIP_CUDA(cudaEventRecord(p.evP, sc));
+    CIP_TRY(hook(jb));
+    const int inner_cols = J1 - jb - 1;
+    if (rem == 0 || inner_cols <= 0) continue;
+    if (inner_cols > 1) {
+      // columns jb+2 .. J1-1 (rows from jb+2 down) on the side stream, after this panel's L21
+      CIP_CUDA(cudaStreamWaitEvent(p.sd, p.evP, 0));
+      GemmArgs c{};
+      c.lower = 0; c.ntm = rem - 1; c.ntn = inner_cols - 1; c.sym = 0;
+      c.x_row0 = j0 + 2 * NB; c.y_row0 = j0 + 2 * NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
+      c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + 2 * NB; c.c_col0 = j0 + 2 * NB; c.alpha = -1.0;
+      CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, p.sd));
+      CIP_CUDA(cudaEventRecord(p.evD[jb & 1], p.sd));
+    }
+    // column jb+1 on the chain; the side stream's update of that column by panel jb-1 comes first
+    if (jb > J0) CIP_CUDA(cudaStreamWaitEvent(sc, p.evD[(jb - 1) & 1], 0));
+    GemmArgs c{};
+    c.lower = 0; c.ntm = rem; c.ntn = 1; c.sym = 0;
+    c.x_row0 = j0 + NB; c.y_row0 = j0 + NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
+    c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + NB; c.c_col0 = j0 + NB; c.alpha = -1.0;
+    CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
+  }
+  return 0;
+}
+// C[rows >= C0 (first row of the column block), columns [C0, C1)] -= L[rows, K0..K1) * L[cols, K0..K1)'   (panel units)
+int update_block_column(const CholPlan& p, int C0, int C1, int K0, int K1, cudaStream_t st) {
+  const int np = p.npanels;
+  GemmArgs c{};
+  c.lower = 0; c.ntm = np - C0; c.ntn = C1 - C0; c.sym = 0;
+  c.x_row0 = C0 * NB; c.y_row0 = C0 * NB; c.x_kq0 = K0 * NB / 4; c.y_kq0 = K0 * NB / 4; c.nk = (K1 - K0) * NB / 32;
+  c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = C0 * NB; c.c_col0 = C0 * NB; c.alpha = -1.0;
+  return launch_gemm_nt(p.mapH, p.mapH, c, st);
+}
+}  // namespace
+
+// Two-level blocked right-looking Cholesky with look-ahead at both levels.
+//   outer panel = OUTER inner panels (512 columns).  Inside an outer panel every 128-wide inner panel is
+//   factored (potrf_diag), solved against all rows below (TRSM as a GEMM with inv(L11)) and applied to the
+//   remaining columns of the outer panel (factor_outer_panel).
+//   The block column of the NEXT outer panel receives the rank-128 update of every inner panel as soon as that
+//   panel is final (stream se, beside the chain), so that when the outer panel is done only the last of those
+//   small updates stands between it and the next potrf -- not a K = 512 update of the whole block column.
+//   The rest of the trailing matrix gets ONE update with K = 512 per outer panel on the caller's stream, which
+//   amortises the C-tile read/write and the pipeline fill that dominate K = 128 tiles.
+int chol_factor(const CholPlan& p, cudaStream_t s) {
+  // The launch sequence below is static for a plan (same kernels, same arguments, same stream fork / join
+  // pattern every time): it is captured once into a CUDA graph and replayed, which takes the per-launch and
+  // per-event-dependency latencies of ~600 stream operations off the panel chain.
+  static const bool use_graph = [] { const char* e = getenv("CIP_CHOL_GRAPH"); return !e || atoi(e) != 0; }();
+  if (use_graph && !p.capturing) {
+    CholPlan& mp = const_cast<CholPlan&>(p);
+    if (!mp.graph_exec && !mp.graph_failed) {
+      cudaGraph_t g = nullptr;
+      mp.capturing = true;
+      cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      int rc = -1;
+      if (e == cudaSuccess) {
+        rc = chol_factor(p, s);
+        e = cudaStreamEndCapture(s, &g);
+      }
+      mp.capturing = false;
+      if (e == cudaSuccess && rc == 0 && g) e = cudaGraphInstantiate(&mp.graph_exec, g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (e != cudaSuccess || rc != 0 || !mp.graph_exec) {
+        cudaGetLastError();
+        mp.graph_exec = nullptr;
+        mp.graph_failed = true;                 // fall back to plain stream launches for this plan
       }
     }
-    CIP_CUDA(cudaEventRecord(p.evT[outer & 1], sc));
+    if (mp.graph_exec) {
+      CIP_CUDA(cudaGraphLaunch(mp.graph_exec, s));
+      g_launches += mp.graph_kernels;
+      return 0;
+    }
+  }
+  const long long launches_before = g_launches.load();
+  struct CountKernels { const CholPlan& p; long long before; ~CountKernels() { if (p.capturing) const_cast<CholPlan&>(p).graph_kernels = g_launches.load() - before; } } counter{p, launches_before};
+  int OUTER = 4;
+  if (const char* env = getenv("CIP_CHOL_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
+  const int smem = POTRF_SMEM;
+  CIP_TRY(ensure_dyn_smem((const void*)potrf_diag_kernel, smem, &g_potrf_attr));
+  cudaStream_t sc = p.sc, se = p.se;
+  const int np = p.npanels;
+  const bool pipe = feed_next_panel(np, p.nranks_hint);
+  CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));
+  CIP_CUDA(cudaEventRecord(p.evS, s));
+  CIP_CUDA(cudaStreamWaitEvent(sc, p.evS, 0));
+  CIP_CUDA(cudaStreamWaitEvent(se, p.evS, 0));
+  int outer = 0;
+  for (int J0 = 0; J0 < np; J0 += OUTER, ++outer) {
+    const int J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
     const int rem = np - J1;
+    const int N1 = (J1 + OUTER < np) ? J1 + OUTER : np;      // the next outer panel is [J1, N1)
+    // its block column was last written by the bulk update of the previous outer panel
+    if (outer > 0 && rem > 0) CIP_CUDA(cudaStreamWaitEvent(se, p.evR[(outer - 1) & 1], 0));
+    CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem, [&](int jb) -> int {
+      if (rem <= 0 || !pipe) return 0;
+      CIP_CUDA(cudaStreamWaitEvent(se, p.evP, 0));
+      return update_block_column(p, J1, N1, jb, jb + 1, se);
+    }));
+    if (rem > 0) {
+      if (!pipe) {                                                         // one K = 512 update instead
+        CIP_CUDA(cudaEventRecord(p.evP, sc));
+        CIP_CUDA(cudaStreamWaitEvent(se, p.evP, 0));
+        CIP_TRY(update_block_column(p, J1, N1, J0, J1, se));
+      }
+      CIP_CUDA(cudaEventRecord(p.evE, se));
+      CIP_CUDA(cudaStreamWaitEvent(sc, p.evE, 0));
+    }
+    CIP_CUDA(cudaEventRecord(p.evT[outer & 1], sc));
     if (rem <= 0) break;
-    const int k0 = J0 * NB, kw = (J1 - J0) * NB, r0 = J1 * NB;
-    // next outer panel's block column first (critical path); it touches tiles the previous bulk
-    // update also wrote, so it has to wait for that one.
-    if (outer > 0) CIP_CUDA(cudaStreamWaitEvent(sc, p.evR[(outer - 1) & 1], 0));
-    const int next_cols = rem < OUTER ? rem : OUTER;
-    GemmArgs c{};
-    c.lower = 0; c.ntm = rem; c.ntn = next_cols; c.sym = 0;
-    c.x_row0 = r0; c.y_row0 = r0; c.x_kq0 = k0 / 4; c.y_kq0 = k0 / 4; c.nk = kw / 32;
-    c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = r0; c.c_col0 = r0; c.alpha = -1.0;
-    CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
-    // bulk trailing update on the caller's stream (K = 512)
+    // bulk trailing update on the caller's stream (K = 512): everything right of the next outer panel
     CIP_CUDA(cudaStreamWaitEvent(s, p.evT[outer & 1], 0));
-    if (rem > OUTER) {
-      const int b0 = r0 + OUTER * NB;
+    if (rem > N1 - J1) {
+      const int b0 = N1 * NB, k0 = J0 * NB, kw = (J1 - J0) * NB;
       GemmArgs u{};
-      u.lower = 1; u.ntm = rem - OUTER; u.ntn = rem - OUTER; u.sym = 1;
+      u.lower = 1; u.ntm = np - N1; u.ntn = np - N1; u.sym = 1;
       u.x_row0 = b0; u.y_row0 = b0; u.x_kq0 = k0 / 4; u.y_kq0 = k0 / 4; u.nk = kw / 32;
       u.Cin = p.H; u.Cout = p.H; u.ldc = p.ld; u.c_row0 = b0; u.c_col0 = b0; u.alpha = -1.0;
       CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, u, s));
@@ -852,93 +950,82 @@ int chol_factor(const CholPlan& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------- distributed (block-cyclic) variant
-namespace {
-// inner factorisation of outer panel [J0, J1) on stream sc (the same sequence chol_factor uses)
-int factor_outer_panel(const CholPlan& p, int J0, int J1, cudaStream_t sc, int smem) {
-  const int np = p.npanels;
-  for (int jb = J0; jb < J1; ++jb) {
-    const int j0 = jb * NB;
-    potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
-    CIP_CHECK_LAUNCH();
-    const int rem = np - jb - 1;
-    if (rem == 0) break;
-    GemmArgs t{};
-    t.lower = 0; t.ntm = rem; t.ntn = 1; t.sym = 0;
-    t.x_row0 = j0 + NB; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = NB / 32;
-    t.Cin = nullptr; t.Cout = p.H; t.ldc = p.ld; t.c_row0 = j0 + NB; t.c_col0 = j0; t.alpha = 1.0;
-    CIP_TRY(launch_gemm_nt(p.mapH, p.mapWinv, t, sc));
-    const int inner_cols = J1 - jb - 1;
-    if (inner_cols > 0) {
-      GemmArgs c{};
-      c.lower = 0; c.ntm = rem; c.ntn = inner_cols; c.sym = 0;
-      c.x_row0 = j0 + NB; c.y_row0 = j0 + NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
-      c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + NB; c.c_col0 = j0 + NB; c.alpha = -1.0;
-      CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
-    }
-  }
-  return 0;
-}
-// C[rows >= first row of outer panel Jc, columns of Jc] -= L[rows, panel J] * L[cols of Jc, panel J]'
-int update_outer_panel(const CholPlan& p, int OUTER, int J, int Jc, cudaStream_t st) {
-  const int np = p.npanels;
-  const int J0 = J * OUTER, J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
-  const int C0 = Jc * OUTER, C1 = (C0 + OUTER < np) ? C0 + OUTER : np;
-  GemmArgs c{};
-  c.lower = 0; c.ntm = np - C0; c.ntn = C1 - C0; c.sym = 0;
-  c.x_row0 = C0 * NB; c.y_row0 = C0 * NB; c.x_kq0 = J0 * NB / 4; c.y_kq0 = J0 * NB / 4; c.nk = (J1 - J0) * NB / 32;
-  c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = C0 * NB; c.c_col0 = C0 * NB; c.alpha = -1.0;
-  return launch_gemm_nt(p.mapH, p.mapH, c, st);
-}
-}  // namespace
-
+// Every rank holds the full matrix buffer; outer panel J is factored by rank J % N and each of its inner panels
+// is broadcast (stream sb) the moment it is final, while the owner's chain goes on.  The rank that factors the
+// NEXT outer panel applies every inner panel to that block column as it arrives (rank-128 updates on its chain
+// stream), exactly as the single-GPU schedule does on `se`; all other owned block columns get one K = 512 update
+// per outer panel.  Every tile therefore receives the same sequence of updates as in chol_factor and the factor
+// is bit-identical to the single-GPU one.
 int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
-  // outer panel width in 128-column panels (measured at C4 on 4 GPUs: 4 -> 39.3 ms, 2 -> 41.1 ms)
   int OUTER = 4;
-  if (const char* env = getenv("CIP_DIST_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
+  if (const char* env = getenv("CIP_CHOL_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
   const NcclApi* api = nccl_api();
   if (!api) return -1;
   const int smem = POTRF_SMEM;
   CIP_TRY(ensure_dyn_smem((const void*)potrf_diag_kernel, smem, &g_potrf_attr));
-  cudaStream_t sc = p.sc;
+  cudaStream_t sc = p.sc, sb = p.sb;
   const int np = p.npanels, NO = (np + OUTER - 1) / OUTER, N = d.nranks, me = d.rank;
+  const bool pipe = feed_next_panel(np, N);
   CIP_CUDA(cudaMemsetAsync(p.info, 0, sizeof(int), s));
   CIP_CUDA(cudaEventRecord(p.evS, s));
   CIP_CUDA(cudaStreamWaitEvent(sc, p.evS, 0));
+  CIP_CUDA(cudaStreamWaitEvent(sb, p.evS, 0));
+  auto bcast_inner = [&](int jb, int owner) -> int {        // column jb (all rows: contiguous in Q4) + inv(L_jj)
+    double* col = p.H + (size_t)(jb * NB / 4) * p.ld * 4;
+    double* w = p.Winv + (size_t)jb * NB * NB;
+    int r = api->GroupStart();
+    if (r == 0) r = api->Broadcast(col, col, (size_t)NB * p.ld, kNcclFloat64, owner, d.comm, sb);
+    if (r == 0) r = api->Broadcast(w, w, (size_t)NB * NB, kNcclFloat64, owner, d.comm, sb);
+    const int r2 = api->GroupEnd();
+    if (r == 0) r = r2;
+    if (r != 0) {
+      set_error("ncclBroadcast failed in the distributed Cholesky: %s", api->GetErrorString(r));
+      return -1;
+    }
+    return 0;
+  };
   int myNext = me;                          // the next outer panel this rank will factor; its updates run on sc
   for (int J = 0; J < NO; ++J) {
     const int owner = J % N;
     const int J0 = J * OUTER, J1 = (J0 + OUTER < np) ? J0 + OUTER : np;
-    if (owner == me) CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem));
-    // broadcast the factored block column (all rows: one contiguous Q4 region) and its inverse blocks
-    {
-      double* panel = p.H + (size_t)(J0 * NB / 4) * p.ld * 4;
-      const size_t cnt = (size_t)(J1 - J0) * NB * p.ld;
-      int r = api->Broadcast(panel, panel, cnt, kNcclFloat64, owner, d.comm, sc);
-      if (r == 0) {
-        double* w = p.Winv + (size_t)J0 * NB * NB;
-        r = api->Broadcast(w, w, (size_t)(J1 - J0) * NB * NB, kNcclFloat64, owner, d.comm, sc);
-      }
-      if (r != 0) {
-        set_error("ncclBroadcast failed in the distributed Cholesky: %s", api->GetErrorString(r));
-        return -1;
+    const int N1 = (J1 + OUTER < np) ? J1 + OUTER : np;
+    const bool feed_next = (myNext == J + 1) && J1 < np;     // this rank factors the next outer panel
+    if (owner == me) {
+      CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem, [&](int jb) -> int {
+        CIP_CUDA(cudaStreamWaitEvent(sb, p.evP, 0));
+        return bcast_inner(jb, owner);
+      }));
+    } else {
+      for (int jb = J0; jb < J1; ++jb) {
+        CIP_TRY(bcast_inner(jb, owner));
+        if (feed_next && pipe) {
+          CIP_CUDA(cudaEventRecord(p.evE, sb));
+          CIP_CUDA(cudaStreamWaitEvent(sc, p.evE, 0));
+          CIP_TRY(update_block_column(p, J1, N1, jb, jb + 1, sc));
+        }
       }
     }
-    CIP_CUDA(cudaEventRecord(p.evT[J & 1], sc));
+    CIP_CUDA(cudaEventRecord(p.evT[J & 1], sb));            // the whole outer panel is here (and, on the owner, factored)
+    CIP_CUDA(cudaStreamWaitEvent(sc, p.evT[J & 1], 0));
     if (owner == me) {
       myNext += N;
       // the new "next" panel has so far been updated on s: order sc after everything s has queued
       CIP_CUDA(cudaEventRecord(p.evR[0], s));
       CIP_CUDA(cudaStreamWaitEvent(sc, p.evR[0], 0));
     }
-    if (myNext < NO && myNext > J) CIP_TRY(update_outer_panel(p, OUTER, J, myNext, sc));
+    // look-ahead block column further away than J+1: one K = 512 update, first, on the chain stream
+    if (myNext < NO && myNext > J && !(feed_next && pipe))
+      CIP_TRY(update_block_column(p, myNext * OUTER, std::min(np, (myNext + 1) * OUTER), J0, J1, sc));
     CIP_CUDA(cudaStreamWaitEvent(s, p.evT[J & 1], 0));
     for (int Jc = me; Jc < NO; Jc += N) {   // owned panels right of J, except the look-ahead one
       if (Jc <= J || Jc == myNext) continue;
-      CIP_TRY(update_outer_panel(p, OUTER, J, Jc, s));
+      CIP_TRY(update_block_column(p, Jc * OUTER, std::min(np, (Jc + 1) * OUTER), J0, J1, s));
     }
   }
   CIP_CUDA(cudaEventRecord(p.evS, sc));
   CIP_CUDA(cudaStreamWaitEvent(s, p.evS, 0));
+  CIP_CUDA(cudaEventRecord(p.evE, sb));
+  CIP_CUDA(cudaStreamWaitEvent(s, p.evE, 0));
   // a failed pivot is only known to the owner of that panel
   int r = api->AllReduce(p.info, p.info, 1, kNcclInt32, kNcclMax, d.comm, s);
   if (r != 0) {

@@ -368,6 +368,7 @@ namespace cip {
 int engine_allreduce(cip_engine* h, double* buf, size_t count) { return allreduce(h, buf, count); }
 int engine_setup_comm(cip_engine* h) {
   if (!h->comm || h->Hp) return 0;
+  h->cholH.nranks_hint = h->nranks;        // the replicated fallback must schedule like the distributed one
   if (const char* env = getenv("CIP_OVERLAP_REDUCE")) if (atoi(env) == 0) return 0;   // A/B switch: plain all-reduce of H4
   CIP_CUDA(cudaSetDevice(h->device));
   const int T = h->n_pad / TILE;

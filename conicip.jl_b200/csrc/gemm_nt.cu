@@ -161,19 +161,28 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int row_base = a.c_row0 + ti * BM + warp_m * 64 + g;
   const int col_base = a.c_col0 + tj * BN + warp_n * 32 + 2 * t;
   double* tm = a.Ctm ? a.Ctm + (size_t)tile * (size_t)(BM * BN) : nullptr;
+  // Cin and Cout are the same buffer for the Cholesky updates, so the compiler has to keep every load behind the
+  // previous store: a load -> add -> store loop is a chain of 32 global-memory latencies (17 us, as long as the
+  // whole K = 128 contraction).  Issue the loads of a column group together, then add and store.
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     const int col = col_base + ni * 8;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-      const int row = row_base + mi * 8;
-      const size_t idx = q4_index(row, col, a.ldc);
-      double2 v = make_double2(0.0, 0.0);
-      if (a.Cin) v = *reinterpret_cast<const double2*>(a.Cin + idx);
-      v.x += alpha * acc[mi][ni][0];
-      v.y += alpha * acc[mi][ni][1];
-      if (tm) *reinterpret_cast<double2*>(tm + q4_index(warp_m * 64 + g + mi * 8, warp_n * 32 + 2 * t + ni * 8, BM)) = v;
-      else *reinterpret_cast<double2*>(a.Cout + idx) = v;
+    for (int mh = 0; mh < 8; mh += 4) {
+      double2 cin[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        cin[mi] = make_double2(0.0, 0.0);
+        if (a.Cin) cin[mi] = *reinterpret_cast<const double2*>(a.Cin + q4_index(row_base + (mh + mi) * 8, col, a.ldc));
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        double2 v = cin[mi];
+        v.x += alpha * acc[mh + mi][ni][0];
+        v.y += alpha * acc[mh + mi][ni][1];
+        if (tm) *reinterpret_cast<double2*>(tm + q4_index(warp_m * 64 + g + (mh + mi) * 8, warp_n * 32 + 2 * t + ni * 8, BM)) = v;
+        else *reinterpret_cast<double2*>(a.Cout + q4_index(row_base + (mh + mi) * 8, col, a.ldc)) = v;
+      }
     }
   }
 }

@@ -101,6 +101,19 @@ struct CholPlan {
   // while the bulk trailing update of the previous panel runs on the caller's stream
   cudaStream_t sc = nullptr;
   cudaEvent_t evT[2] = {}, evR[2] = {}, evS = nullptr;
+  // inner look-ahead: the update of the NEXT 128-column panel stays on the chain (sc), the update of the other
+  // columns of the outer panel runs beside it on sd
+  cudaStream_t sd = nullptr;
+  cudaEvent_t evD[2] = {}, evP = nullptr;
+  // outer look-ahead: rank-128 updates of the next outer panel's block column, one per finished inner panel (se);
+  // distributed variant: broadcasts of the inner panels (sb)
+  cudaStream_t se = nullptr, sb = nullptr;
+  cudaEvent_t evE = nullptr;
+  // chol_factor's launch sequence as a CUDA graph (captured on first use)
+  cudaGraphExec_t graph_exec = nullptr;
+  bool capturing = false, graph_failed = false;
+  long long graph_kernels = 0;
+  int nranks_hint = 1;      // ranks sharing the factorisation (set by the engine once a communicator exists)
   // persistent triangular sweeps: work units (device), partial sums of split block rows, error flag
   void *units_fwd = nullptr, *units_bwd = nullptr;
   int nunits = 0, maxseg = 1;

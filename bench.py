@@ -488,9 +488,14 @@ def run_b200(args, n, m):
         m_loc = hprob["A"].shape[0]
         c_vec, b_loc, d_vec = T(hprob["c"]), T(hprob["b"]), (T(hprob["d"]) if p else None)
     t_setup = time.time() - t_setup
+    if D.rank == 0:
+        print(f"[bench] setup {t_setup:.1f} s ({cfg}, n={n}, m={m}, gpus={args.gpus}, "
+              f"{'single process' if single_process else 'torchrun' if D.world > 1 else 'one GPU'})", file=sys.stderr, flush=True)
 
     ms_step, clocks, launches, ph = timed_unit_loop(torch, D, eng, pts, rhs, args.steps, args.warmup, True)
     value = 1e3 / ms_step
+    if D.rank == 0:
+        print(f"[bench] device-resident: {ms_step:.2f} ms/step", file=sys.stderr, flush=True)
     e2e = e2e_unit_loop(torch, D, eng, pts, rhs, max(2, min(args.steps, 3)), n, m_loc, p)
 
     # ---- roofline of the dominant kernel (gemm_nt as the SYRK), CUDA events recorded by the library on the

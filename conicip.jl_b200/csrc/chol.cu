@@ -515,6 +515,173 @@ potrf_diag_kernel(double* __restrict__ H, int ld, int j0, double* __restrict__ W
 #endif
 }
 
+// ---------------------------------------------------------------- panel head (the chain between two potrf's)
+// After potrf_diag(jb) the next potrf only waits for ONE block row of work: T = A(jb+1, jb) inv(L_jj)' (the TRSM of
+// that row) and A(jb+1, jb+1) -= T T' (its diagonal update).  As 128x128 tiles of the general GEMM kernel these are
+// two single-CTA launches of ~20 us each -- a 128^3 product is 17 us on one SM at the DMMA peak -- so the chain
+// between two factorisations was longer than the factorisation itself.  This kernel spreads the block row over a
+// cluster of eight CTAs (16 rows each): phase 1 the strip of T (triangular: only k <= c contributes; the column
+// groups are paired so that every scheduler gets the same share), cluster barrier, phase 2 the strip's rows of the
+// diagonal update against the strips of the lower-numbered CTAs, read back through L2.  DMMA.8x8x4 fragments come
+// straight from k-major shared arrays whose leading dimensions are = 8 mod 16, which spreads the 32 lanes of a
+// fragment over all banks (two wavefronts for 256 bytes: the minimum).
+constexpr int HEAD_CTAS = 8;
+constexpr int HEAD_THREADS = 256;
+constexpr int HS = NB / HEAD_CTAS;           // 16 rows per CTA
+constexpr int WLD = NB + 8;                  // k-major inverse:  Ws[k * WLD + c] = inv(L)(c, k);  later Tf[c * WLD + row]
+constexpr int SLD = HS + 8;                  // k-major strip:    As[k * SLD + i]
+constexpr int HEAD_SMEM = (NB * WLD + NB * SLD) * (int)sizeof(double);
+static_assert(WLD % 16 == 8 && SLD % 16 == 8, "bank-conflict-free DMMA fragments need leading dimensions = 8 mod 16");
+
+__global__ void __cluster_dims__(HEAD_CTAS, 1, 1) __launch_bounds__(HEAD_THREADS, 1)
+chol_head_kernel(double* H, int ld, int j0, const double* __restrict__ W) {
+  extern __shared__ __align__(16) double hsm[];
+  double* Ws = hsm;                          // [128 k][WLD]
+  double* As = Ws + NB * WLD;                // [128 k][SLD]
+  double* Tf = Ws;                           // [128 c][WLD]: T of the block row (own strip + the lower ones); phase 2 only
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;     // DMMA fragment coordinates
+  const int q = blockIdx.x % HEAD_CTAS;      // strip of this CTA
+  const int r0 = j0 + NB + HS * q;           // first matrix row of the strip
+  // ---- loads (every load of a batch is issued before the first store: a load -> store loop is a chain of global
+  //      latencies): the strip of A(jb+1, jb) and inv(L_jj), both transposed to k-major
+  {
+    double2 a0[2], a1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {                              // strip of A: 16 rows x 32 quads
+      const int e = tid + u * HEAD_THREADS, i = e & (HS - 1), kq = e >> 4;
+      const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + kq) * ld + r0 + i) * 4);
+      a0[u] = p[0]; a1[u] = p[1];
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                     // inv(L_jj): 128 rows x 32 quads, two batches of eight
+      double2 w0[8], w1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + (half * 8 + u) * HEAD_THREADS, c = e & (NB - 1), kq = e >> 7;   // quad kq of row c: inv(L)(c, 4kq ..)
+        const double2* p = reinterpret_cast<const double2*>(W + ((size_t)kq * NB + c) * 4);
+        w0[u] = __ldg(p); w1[u] = __ldg(p + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = tid + (half * 8 + u) * HEAD_THREADS, c = e & (NB - 1), kq = e >> 7;
+        Ws[(4 * kq + 0) * WLD + c] = w0[u].x; Ws[(4 * kq + 1) * WLD + c] = w0[u].y;
+        Ws[(4 * kq + 2) * WLD + c] = w1[u].x; Ws[(4 * kq + 3) * WLD + c] = w1[u].y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * HEAD_THREADS, i = e & (HS - 1), kq = e >> 4;
+      As[(4 * kq + 0) * SLD + i] = a0[u].x; As[(4 * kq + 1) * SLD + i] = a0[u].y;
+      As[(4 * kq + 2) * SLD + i] = a1[u].x; As[(4 * kq + 3) * SLD + i] = a1[u].y;
+    }
+  }
+  __syncthreads();
+  // ---- phase 1: T(i, c) = sum_{k <= c} A(i, k) inv(L)(c, k).  Warp = 16 columns x 16 rows (2 x 2 tiles); the
+  //      triangular k range grows with the column group, so warps w and w + 4 (same scheduler) take groups whose
+  //      ranges add up to the same total.
+  {
+    const int cg = (w < 4) ? 2 * w : 2 * (7 - w) + 1;
+    const int c0 = 16 * cg;
+    double acc[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    const int kq_end = (c0 + 15) >> 2;                          // last quad that meets a non-zero of these columns
+#pragma unroll 4
+    for (int kq = 0; kq <= kq_end; ++kq) {
+      const double* ap = As + (4 * kq + t) * SLD + g;
+      const double* wp = Ws + (4 * kq + t) * WLD + c0 + g;
+      const double a0 = ap[0], a1 = ap[8], b0 = wp[0], b1 = wp[8];
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+    __syncthreads();                                            // Ws is dead from here: Tf takes its place
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int i = 8 * x + g, c = c0 + 8 * y + 2 * t;
+        // tile (jb+1, jb) of the factor itself ...
+        *reinterpret_cast<double2*>(H + ((size_t)((j0 + c) >> 2) * ld + r0 + i) * 4 + (c & 3)) =
+            make_double2(acc[x][y][0], acc[x][y][1]);
+        // ... and the own rows of Tf
+        Tf[c * WLD + HS * q + i] = acc[x][y][0];
+        Tf[(c + 1) * WLD + HS * q + i] = acc[x][y][1];
+      }
+  }
+  // ---- every strip of T visible to the cluster (it was written to global memory above)
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // ---- phase 2 operands: the rows of the lower-numbered strips back from L2 (never read by this SM before, so no
+  //      stale L1 line), and -- requested now, needed at the very end -- this warp's tiles of S = A(jb+1, jb+1)
+  const int nct = 2 * (q + 1);                                  // 8-column tiles of S left of / on the diagonal
+  double2 cv[2][2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int ct = w + 8 * u;
+      cv[x][u] = make_double2(0.0, 0.0);
+      if (ct < nct) {
+        const int i = 8 * x + g, j = 8 * ct + 2 * t;
+        cv[x][u] = *reinterpret_cast<const double2*>(H + ((size_t)((j0 + NB + j) >> 2) * ld + r0 + i) * 4 + (j & 3));
+      }
+    }
+  for (int b0 = 0; b0 < 2 * q; b0 += 2) {                       // HS * q rows x 32 quads = 2 q rounds of 256, two per batch
+    double2 t0[2], t1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + (b0 + u) * HEAD_THREADS, i = e % (HS * q), cq = e / (HS * q);
+      const double2* p = reinterpret_cast<const double2*>(H + ((size_t)(j0 / 4 + cq) * ld + j0 + NB + i) * 4);
+      t0[u] = __ldcg(p); t1[u] = __ldcg(p + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + (b0 + u) * HEAD_THREADS, i = e % (HS * q), cq = e / (HS * q);
+      Tf[(4 * cq + 0) * WLD + i] = t0[u].x; Tf[(4 * cq + 1) * WLD + i] = t0[u].y;
+      Tf[(4 * cq + 2) * WLD + i] = t1[u].x; Tf[(4 * cq + 3) * WLD + i] = t1[u].y;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: S(i, j) -= sum_c T(i, c) T(j, c) for the strip's rows i and the columns j < 16 (q + 1)
+  if (w < nct) {
+    const bool two = (w + 8) < nct;
+    double acc[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) acc[x][u][0] = acc[x][u][1] = 0.0;
+#pragma unroll 4
+    for (int cq = 0; cq < NB / 4; ++cq) {
+      const double* tp = Tf + (4 * cq + t) * WLD + g;
+      const double a0 = tp[HS * q], a1 = tp[HS * q + 8];
+      const double b0 = tp[8 * w], b1 = two ? tp[8 * (w + 8)] : 0.0;
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      if (two) {
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ct = w + 8 * u;
+        if (ct < nct) {
+          const int i = 8 * x + g, j = 8 * ct + 2 * t;
+          *reinterpret_cast<double2*>(H + ((size_t)((j0 + NB + j) >> 2) * ld + r0 + i) * 4 + (j & 3)) =
+              make_double2(cv[x][u].x - acc[x][u][0], cv[x][u].y - acc[x][u][1]);
+        }
+      }
+  }
+}
+std::atomic<unsigned long long> g_head_attr{0};
+
 // ---------------------------------------------------------------- triangular sweeps (K3)
 // One persistent launch per direction (forward L y = b, backward L' x = y) instead of one launch per
 // 128-column panel.  Block row b of the triangular matrix is owned by CTAs ("units"): its off-diagonal tiles
@@ -732,8 +899,10 @@ int chol_make_plan(CholPlan* p, double* H, int n_pad, double* Winv, int* info) {
   CIP_CUDA(cudaStreamCreateWithPriority(&p->sc, cudaStreamNonBlocking, hi));
   CIP_CUDA(cudaStreamCreateWithPriority(&p->sd, cudaStreamNonBlocking, hi));
   CIP_CUDA(cudaStreamCreateWithPriority(&p->se, cudaStreamNonBlocking, hi));
+  CIP_CUDA(cudaStreamCreateWithPriority(&p->sf, cudaStreamNonBlocking, hi));
   CIP_CUDA(cudaStreamCreateWithPriority(&p->sb, cudaStreamNonBlocking, hi));
-  for (auto* e : {&p->evT[0], &p->evT[1], &p->evR[0], &p->evR[1], &p->evS, &p->evD[0], &p->evD[1], &p->evP, &p->evE})
+  for (auto* e : {&p->evT[0], &p->evT[1], &p->evR[0], &p->evR[1], &p->evS, &p->evD[0], &p->evD[1], &p->evP, &p->evE,
+                  &p->evC, &p->evH, &p->evUc[0], &p->evUc[1], &p->evUo[0], &p->evUo[1]})
     CIP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   // ---- work units of the persistent triangular sweeps (see trsv_sweep_kernel)
   {
@@ -781,10 +950,12 @@ void chol_free_plan(CholPlan* p) {
   p->graph_exec = nullptr;
   if (p->sd) cudaStreamDestroy(p->sd);
   if (p->se) cudaStreamDestroy(p->se);
+  if (p->sf) cudaStreamDestroy(p->sf);
   if (p->sb) cudaStreamDestroy(p->sb);
-  for (auto e : {p->evT[0], p->evT[1], p->evR[0], p->evR[1], p->evS, p->evD[0], p->evD[1], p->evP, p->evE})
+  for (auto e : {p->evT[0], p->evT[1], p->evR[0], p->evR[1], p->evS, p->evD[0], p->evD[1], p->evP, p->evE, p->evC, p->evH,
+                 p->evUc[0], p->evUc[1], p->evUo[0], p->evUo[1]})
     if (e) cudaEventDestroy(e);
-  p->sc = nullptr; p->sd = nullptr; p->se = nullptr; p->sb = nullptr;
+  p->sc = nullptr; p->sd = nullptr; p->se = nullptr; p->sb = nullptr; p->sf = nullptr;
   for (void* q : {(void*)p->units_fwd, (void*)p->units_bwd, (void*)p->sweep_part, (void*)p->sweep_err})
     if (q) cudaFree(q);
   p->units_fwd = p->units_bwd = nullptr; p->sweep_part = nullptr; p->sweep_err = nullptr;
@@ -809,39 +980,80 @@ bool feed_next_panel(int npanels, int nranks) {
 template <typename Hook>
 int factor_outer_panel(const CholPlan& p, int J0, int J1, cudaStream_t sc, int smem, Hook hook) {
   const int np = p.npanels;
+  static const bool use_head = [] { const char* e = getenv("CIP_CHOL_HEAD"); return !e || atoi(e) != 0; }();
+  CIP_TRY(ensure_dyn_smem((const void*)chol_head_kernel, HEAD_SMEM, &g_head_attr));
+  cudaStream_t sd = p.sd, sf = p.sf;
+  auto trsm = [&](int jb, int first_row_panel, cudaStream_t st) -> int {     // L(i, jb) = A(i, jb) inv(L_jj)' for block rows i >= first
+    const int j0 = jb * NB, ntm = np - first_row_panel;
+    if (ntm <= 0) return 0;
+    GemmArgs t{};
+    t.lower = 0; t.ntm = ntm; t.ntn = 1; t.sym = 0;
+    t.x_row0 = first_row_panel * NB; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = NB / 32;
+    t.Cin = nullptr; t.Cout = p.H; t.ldc = p.ld; t.c_row0 = first_row_panel * NB; t.c_col0 = j0; t.alpha = 1.0;
+    t.y_lower_tri = 1;
+    return launch_gemm_nt(p.mapH, p.mapWinv, t, st);
+  };
+  auto update = [&](int jb, int row_panel, int col_panel0, int ncols, cudaStream_t st) -> int {   // rank-128 update by panel jb
+    const int j0 = jb * NB, ntm = np - row_panel;
+    if (ntm <= 0 || ncols <= 0) return 0;
+    GemmArgs c{};
+    c.lower = 0; c.ntm = ntm; c.ntn = ncols; c.sym = 0;
+    c.x_row0 = row_panel * NB; c.y_row0 = col_panel0 * NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
+    c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = row_panel * NB; c.c_col0 = col_panel0 * NB; c.alpha = -1.0;
+    return launch_gemm_nt(p.mapH, p.mapH, c, st);
+  };
+  bool uc_prev = false, uo_prev = false;       // off-chain updates of the previous inner panel still to be awaited
   for (int jb = J0; jb < J1; ++jb) {
     const int j0 = jb * NB;
+    const int rem = np - jb - 1;
+    const int inner_cols = J1 - jb - 1;
     potrf_diag_kernel<<<1, PT, smem, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB, p.info);
     CIP_CHECK_LAUNCH();
-    const int rem = np - jb - 1;
-    if (rem > 0) {
-      GemmArgs t{};   // L21 = A21 * inv(L11)'
-      t.lower = 0; t.ntm = rem; t.ntn = 1; t.sym = 0;
-      t.x_row0 = j0 + NB; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = NB / 32;
-      t.Cin = nullptr; t.Cout = p.H; t.ldc = p.ld; t.c_row0 = j0 + NB; t.c_col0 = j0; t.alpha = 1.0;
-      CIP_TRY(launch_gemm_nt(p.mapH, p.mapWinv, t, sc));
-    }
     CIP_CUDA(cudaEventRecord(p.evP, sc));
-    CIP_TRY(hook(jb));
-    const int inner_cols = J1 - jb - 1;
-    if (rem == 0 || inner_cols <= 0) continue;
-    if (inner_cols > 1) {
-      // columns jb+2 .. J1-1 (rows from jb+2 down) on the side stream, after this panel's L21
-      CIP_CUDA(cudaStreamWaitEvent(p.sd, p.evP, 0));
-      GemmArgs c{};
-      c.lower = 0; c.ntm = rem - 1; c.ntn = inner_cols - 1; c.sym = 0;
-      c.x_row0 = j0 + 2 * NB; c.y_row0 = j0 + 2 * NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
-      c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + 2 * NB; c.c_col0 = j0 + 2 * NB; c.alpha = -1.0;
-      CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, p.sd));
-      CIP_CUDA(cudaEventRecord(p.evD[jb & 1], p.sd));
+    // everything below reads tiles that the previous panel's off-chain updates wrote
+    if (uc_prev) CIP_CUDA(cudaStreamWaitEvent(sc, p.evUc[(jb - 1) & 1], 0));
+    if (uo_prev) CIP_CUDA(cudaStreamWaitEvent(sc, p.evUo[(jb - 1) & 1], 0));
+    const bool uo_before = uo_prev;
+    const bool head = use_head && inner_cols >= 1 && rem >= 1;
+    if (!head) {
+      // last inner panel of the outer panel (or head disabled): the whole column on the chain, as one TRSM
+      CIP_TRY(trsm(jb, jb + 1, sc));
+      CIP_CUDA(cudaEventRecord(p.evC, sc));
+      CIP_TRY(hook(jb));
+      uc_prev = uo_prev = false;
+      if (rem == 0 || inner_cols <= 0) continue;
+      if (inner_cols > 1) {                     // (head disabled) other columns beside the chain, next column on it
+        CIP_CUDA(cudaStreamWaitEvent(sf, p.evC, 0));
+        CIP_TRY(update(jb, jb + 2, jb + 2, inner_cols - 1, sf));
+        CIP_CUDA(cudaEventRecord(p.evUo[jb & 1], sf));
+        uo_prev = true;
+      }
+      CIP_TRY(update(jb, jb + 1, jb + 1, 1, sc));
+      continue;
     }
-    // column jb+1 on the chain; the side stream's update of that column by panel jb-1 comes first
-    if (jb > J0) CIP_CUDA(cudaStreamWaitEvent(sc, p.evD[(jb - 1) & 1], 0));
-    GemmArgs c{};
-    c.lower = 0; c.ntm = rem; c.ntn = 1; c.sym = 0;
-    c.x_row0 = j0 + NB; c.y_row0 = j0 + NB; c.x_kq0 = j0 / 4; c.y_kq0 = j0 / 4; c.nk = NB / 32;
-    c.Cin = p.H; c.Cout = p.H; c.ldc = p.ld; c.c_row0 = j0 + NB; c.c_col0 = j0 + NB; c.alpha = -1.0;
-    CIP_TRY(launch_gemm_nt(p.mapH, p.mapH, c, sc));
+    // ---- chain: block row jb+1 only (its TRSM tile and its diagonal update), on a cluster of four CTAs
+    chol_head_kernel<<<HEAD_CTAS, HEAD_THREADS, HEAD_SMEM, sc>>>(p.H, p.ld, j0, p.Winv + (size_t)jb * NB * NB);
+    CIP_CHECK_LAUNCH();
+    CIP_CUDA(cudaEventRecord(p.evH, sc));
+    // ---- beside the chain: the rest of the column, then the updates that need it
+    CIP_CUDA(cudaStreamWaitEvent(sd, p.evP, 0));
+    CIP_TRY(trsm(jb, jb + 2, sd));                                   // rows jb+2 ..
+    CIP_CUDA(cudaStreamWaitEvent(sd, p.evH, 0));                     // + L(jb+1, jb) from the head: column jb is final
+    CIP_CUDA(cudaEventRecord(p.evC, sd));
+    CIP_TRY(hook(jb));
+    uc_prev = uo_prev = false;
+    if (rem >= 2) {
+      if (uo_before) CIP_CUDA(cudaStreamWaitEvent(sd, p.evUo[(jb - 1) & 1], 0));   // column jb+1 was last written there
+      CIP_TRY(update(jb, jb + 2, jb + 1, 1, sd));                    // column jb+1, rows jb+2 ..
+      CIP_CUDA(cudaEventRecord(p.evUc[jb & 1], sd));
+      uc_prev = true;
+      if (inner_cols >= 2) {
+        CIP_CUDA(cudaStreamWaitEvent(sf, p.evC, 0));
+        CIP_TRY(update(jb, jb + 2, jb + 2, inner_cols - 1, sf));     // columns jb+2 .. J1-1, rows jb+2 ..
+        CIP_CUDA(cudaEventRecord(p.evUo[jb & 1], sf));
+        uo_prev = true;
+      }
+    }
   }
   return 0;
 }
@@ -918,7 +1130,7 @@ int chol_factor(const CholPlan& p, cudaStream_t s) {
     if (outer > 0 && rem > 0) CIP_CUDA(cudaStreamWaitEvent(se, p.evR[(outer - 1) & 1], 0));
     CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem, [&](int jb) -> int {
       if (rem <= 0 || !pipe) return 0;
-      CIP_CUDA(cudaStreamWaitEvent(se, p.evP, 0));
+      CIP_CUDA(cudaStreamWaitEvent(se, p.evC, 0));
       return update_block_column(p, J1, N1, jb, jb + 1, se);
     }));
     if (rem > 0) {
@@ -992,7 +1204,7 @@ int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
     const bool feed_next = (myNext == J + 1) && J1 < np;     // this rank factors the next outer panel
     if (owner == me) {
       CIP_TRY(factor_outer_panel(p, J0, J1, sc, smem, [&](int jb) -> int {
-        CIP_CUDA(cudaStreamWaitEvent(sb, p.evP, 0));
+        CIP_CUDA(cudaStreamWaitEvent(sb, p.evC, 0));
         return bcast_inner(jb, owner);
       }));
     } else {

@@ -1063,7 +1063,8 @@ int cip_stats(cip_handle h, cip_stats_t* out) {
   CIP_TRY(check(h));
   if (h->multi) return multi_stats(h, out);
   float ms = 0;
-  if (h->st.solves > 0 && cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->st.ms_solve = ms;
+  if (h->st.solves > 0 && cudaEventSynchronize(h->ev[7]) == cudaSuccess &&
+      cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->st.ms_solve = ms;
   else cudaGetLastError();
   h->st.device_bytes = h->bytes;
   h->st.kernel_launches = cip::g_launches;

@@ -128,6 +128,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const double* st = tiles + (size_t)s * STAGE_DOUBLES;
     const double* xs = st + x_off;
     const double* ys = st + y_off;
+    if (!(a.y_lower_tri && kt - kt0 > warp_n))
 #pragma unroll
     for (int q = 0; q < KQ; ++q) {
       double av[8], bv[4];

@@ -46,6 +46,9 @@ struct GemmArgs {
   // the last range, whose all-reduce cannot hide behind compute, is the small tip of the triangle.
   int tile_begin, tile_count, reverse;
   double* Ctm;
+  // Y tile is lower triangular (Y[j, k] = 0 for k > j, tile-aligned, nk = 4: the inverse of a diagonal block in
+  // the Cholesky TRSM): a consumer warp skips the k tiles that only meet zeros of its 32 columns
+  int y_lower_tri;
 };
 constexpr long long GEMM_WS_DOUBLES = 2048ll * 128 * 128;   // 2048 partial tiles (268 MB)
 

@@ -109,6 +109,9 @@ struct CholPlan {
   // distributed variant: broadcasts of the inner panels (sb)
   cudaStream_t se = nullptr, sb = nullptr;
   cudaEvent_t evE = nullptr;
+  // panel head on the chain (chol_head_kernel), the rest of the column (sd) and the other columns (sf) beside it
+  cudaStream_t sf = nullptr;
+  cudaEvent_t evC = nullptr, evH = nullptr, evUc[2] = {}, evUo[2] = {};
   // chol_factor's launch sequence as a CUDA graph (captured on first use)
   cudaGraphExec_t graph_exec = nullptr;
   bool capturing = false, graph_failed = false;

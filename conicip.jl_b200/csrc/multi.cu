@@ -285,6 +285,13 @@ int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq,
       if (slice_csc(As, M->row_lo[r], M->row_hi[r], &slices[r]) != 0) { multi_destroy(h); return -1; }
   for (int r = 0; r < N; ++r) M->th.emplace_back(&Multi::worker, M, r);
   int rc = M->run([&](int r) {
+    // direct peer copies for slabs that arrive as device pointers on another GPU (ignored where unsupported)
+    for (int q = 0; q < N; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, M->dev[r], M->dev[q]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(M->dev[q], 0);
+      cudaGetLastError();
+    }
     cip_options o{};
     memcpy(&o, opts, std::min<size_t>(sizeof(o), (size_t)opts->struct_size));
     o.struct_size = sizeof(o);

@@ -27,119 +27,10 @@ __device__ __forceinline__ double group_sum(double v, double* sm) {
   return t;
 }
 
-template <int G>
-__device__ __forceinline__ bool q_cone_of(const ConeDesc& c, int& ci, int& off, int& dim, int& lid) {
-  const int per_block = blockDim.x / G;
-  const int qi = blockIdx.x * per_block + threadIdx.x / G;
-  lid = threadIdx.x % G;
-  if (qi >= c.nq) return false;   // G==256: whole block exits together; G==32: whole warp
-  ci = c.qlist[qi];
-  off = c.off[ci];
-  dim = c.off[ci + 1] - off;
-  return true;
-}
-
 // order-preserving map double -> uint64 for atomicMin
 __device__ __forceinline__ unsigned long long dkey(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-
-// ================================================================= NT scaling
-__global__ void nt_r_kernel(ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
-                            Scaling Fi, double* __restrict__ lambda) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
-    const int ty = c.type[c.row_cone[i]];
-    if (ty == CIP_CONE_S) { F.a[i] = 0.0; F.b[i] = 0.0; Fi.a[i] = 0.0; Fi.b[i] = 0.0; }
-    if (ty != CIP_CONE_R) continue;
-    const double f = sqrt(s[i] / v[i]);          // Diagonal(sqrt.(yI./xI)), src/ConicIP.jl:598
-    F.a[i] = f;
-    F.b[i] = 0.0;
-    Fi.a[i] = 1.0 / f;
-    Fi.b[i] = 0.0;
-    lambda[i] = f * v[i];
-  }
-}
-
-// all rows in R cones (LP / QP): no per-row cone lookup, two rows per iteration with 16-byte accesses
-__global__ void nt_r_all_kernel(int m, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
-                                Scaling Fi, double* __restrict__ lambda) {
-  const int m2 = m >> 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
-    const double2 vv = reinterpret_cast<const double2*>(v)[i], ss = reinterpret_cast<const double2*>(s)[i];
-    const double2 f = make_double2(sqrt(ss.x / vv.x), sqrt(ss.y / vv.y));
-    reinterpret_cast<double2*>(F.a)[i] = f;
-    reinterpret_cast<double2*>(F.b)[i] = make_double2(0.0, 0.0);
-    reinterpret_cast<double2*>(Fi.a)[i] = make_double2(1.0 / f.x, 1.0 / f.y);
-    reinterpret_cast<double2*>(Fi.b)[i] = make_double2(0.0, 0.0);
-    reinterpret_cast<double2*>(lambda)[i] = make_double2(f.x * vv.x, f.y * vv.y);
-  }
-  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int i = m - 1;
-    const double f = sqrt(s[i] / v[i]);
-    F.a[i] = f; F.b[i] = 0.0; Fi.a[i] = 1.0 / f; Fi.b[i] = 0.0; lambda[i] = f * v[i];
-  }
-}
-
-__global__ void nt_kind_kernel(ConeDesc c, Scaling F, Scaling Fi) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.ncones) return;
-  if (c.type[i] == CIP_CONE_R) {
-    F.kind[i] = CIP_BLK_DIAG;  Fi.kind[i] = CIP_BLK_DIAG;  F.D[i] = 0.0;  Fi.D[i] = 0.0;
-  } else if (c.type[i] == CIP_CONE_Q) {
-    F.kind[i] = CIP_BLK_WOODBURY;  Fi.kind[i] = CIP_BLK_WOODBURY;   // D set by nt_q_kernel
-  }
-}
-
-template <int G>
-__global__ void nt_q_kernel(ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F,
-                            Scaling Fi, double* __restrict__ lambda) {
-  __shared__ double sm[8];
-  int ci, off, dim, lid;
-  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
-  const double* z = v + off;     // nestod_soc(z = v_I, s = s_I), src/ConicIP.jl:599
-  const double* sv = s + off;
-  double zz = 0, ss = 0;
-  for (int i = lid; i < dim; i += G) { zz += z[i] * z[i]; ss += sv[i] * sv[i]; }
-  zz = group_sum<G>(zz, sm);
-  ss = group_sum<G>(ss, sm);
-  const double qfz = 2 * z[0] * z[0] - zz;       // QF, src/ConicIP.jl:160
-  const double qfs = 2 * sv[0] * sv[0] - ss;
-  const double beta = sqrt(sqrt(qfs / qfz));     // (QF(s)/QF(z))^(1/4)
-  // normalisation by multiplication with the reciprocals (one division per cone instead of four per
-  // element; differs from the reference's elementwise z/sqrt(QF(z)) in the last bit only)
-  const double irz = 1.0 / sqrt(qfz), irs = 1.0 / sqrt(qfs);
-  double zs = 0;
-  for (int i = lid; i < dim; i += G) zs += (z[i] * irz) * (sv[i] * irs);
-  zs = group_sum<G>(zs, sm);
-  const double gamma = sqrt((1 + zs) / 2);
-  const double inv2g = 1.0 / (2.0 * gamma);
-  // w = (s + Jz)/(2 gamma); w1 += 1; w *= sqrt(2 beta)/sqrt(2 w1)
-  const double w1 = inv2g * (sv[0] * irs + z[0] * irz) + 1.0;
-  const double scal = sqrt(2 * beta) / sqrt(2 * w1);
-  double wv = 0, bib = 0;
-  for (int i = lid; i < dim; i += G) {
-    const double zi = z[i] * irz, si = sv[i] * irs;
-    const double w = (i == 0) ? w1 * scal : (inv2g * (si - zi)) * scal;
-    const double a = (i == 0) ? -beta : beta;
-    F.a[off + i] = a;
-    F.b[off + i] = w;
-    const double ia = 1.0 / a;                   // Woodbury inverse: W = inv(A), X = W*B
-    Fi.a[off + i] = ia;
-    Fi.b[off + i] = ia * w;
-    wv += w * z[i];
-    bib += w * (ia * w);
-  }
-  wv = group_sum<G>(wv, sm);
-  bib = group_sum<G>(bib, sm);
-  for (int i = lid; i < dim; i += G) {                             // lambda = F*v, w recomputed (no re-read)
-    const double w = (i == 0) ? w1 * scal : (inv2g * (sv[i] * irs - z[i] * irz)) * scal;
-    lambda[off + i] = ((i == 0) ? -beta : beta) * z[i] + w * wv;
-  }
-  if (lid == 0) {
-    F.D[ci] = 1.0;
-    Fi.D[ci] = 1.0 / (-1.0 - bib);               // Z = inv(-inv(D) - B'X), D = 1
-  }
 }
 
 // generic inverse of a flattened scaling (used by cip_factor / cip_set_scaling)
@@ -172,94 +63,7 @@ __global__ void inv_wood_kernel(ConeDesc c, Scaling F, Scaling Fi) {
   if (lane == 0) Fi.D[ci] = 1.0 / (-1.0 / F.D[ci] - bib);
 }
 
-// ================================================================= block apply
-__global__ void apply_diag_kernel(int m, const double* __restrict__ a, const double* __restrict__ x,
-                                  double* __restrict__ y) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) y[i] = a[i] * x[i];
-}
-__global__ void apply_wood_kernel(ConeDesc c, Scaling F, const double* __restrict__ x, double* __restrict__ y) {
-  const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (ci >= c.ncones || F.kind[ci] != CIP_BLK_WOODBURY) return;
-  const int off = c.off[ci], dim = c.off[ci + 1] - off;
-  double bx = 0;
-  for (int i = lane; i < dim; i += 32) bx += F.b[off + i] * x[off + i];
-  bx = warp_sum(bx) * F.D[ci];
-  for (int i = lane; i < dim; i += 32) y[off + i] += F.b[off + i] * bx;   // A*x + B*(D*(B'x))
-}
-
-// ================================================================= Jordan product / division
-__global__ void prod_r_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
-                              double* __restrict__ o, int divide) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
-    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
-    o[i] = divide ? x[i] / y[i] : x[i] * y[i];   // drp! / xrp!, src/ConicIP.jl:305-315
-  }
-}
-__global__ void prod_r_all_kernel(int m, const double* __restrict__ x, const double* __restrict__ y,
-                                  double* __restrict__ o, int divide) {
-  const int m2 = m >> 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
-    const double2 a = reinterpret_cast<const double2*>(x)[i], b = reinterpret_cast<const double2*>(y)[i];
-    reinterpret_cast<double2*>(o)[i] = divide ? make_double2(a.x / b.x, a.y / b.y) : make_double2(a.x * b.x, a.y * b.y);
-  }
-  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) o[m - 1] = divide ? x[m - 1] / y[m - 1] : x[m - 1] * y[m - 1];
-}
-
-template <int G>
-__global__ void prod_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
-                              double* __restrict__ o) {
-  __shared__ double sm[8];
-  int ci, off, dim, lid;
-  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
-  const double* xp = x + off;
-  const double* yp = y + off;
-  double d = 0;
-  for (int i = lid; i < dim; i += G) d += xp[i] * yp[i];
-  d = group_sum<G>(d, sm);
-  const double x0 = xp[0], y0 = yp[0];
-  for (int i = lid; i < dim; i += G) o[off + i] = (i == 0) ? d : x0 * yp[i] + y0 * xp[i];   // xsoc!, :340-345
-}
-template <int G>
-__global__ void div_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ y,
-                             double* __restrict__ o) {
-  // o = arrow(y)^-1 x   (dsoc!(y=x_arg, x=y_arg, o), src/ConicIP.jl:317-338)
-  __shared__ double sm[8];
-  int ci, off, dim, lid;
-  if (!q_cone_of<G>(c, ci, off, dim, lid)) return;
-  const double* num = x + off;   // reference's "y" (x1, xb)
-  const double* arr = y + off;   // reference's "x" (y1, yb)
-  double ybyb = 0, ybxb = 0;
-  for (int i = lid; i < dim; i += G) {
-    if (i > 0) { ybyb += arr[i] * arr[i]; ybxb += arr[i] * num[i]; }
-  }
-  ybyb = group_sum<G>(ybyb, sm);
-  ybxb = group_sum<G>(ybxb, sm);
-  const double y1 = arr[0], x1 = num[0];
-  const double alpha = y1 * y1 - ybyb;
-  const double b1 = (-x1 / alpha) + ybxb / (y1 * alpha);
-  const double b2 = 1.0 / y1;
-  for (int i = lid; i < dim; i += G)
-    o[off + i] = (i == 0) ? (y1 * x1 - ybxb) / alpha : arr[i] * b1 + num[i] * b2;
-}
-
-// ================================================================= max step
-__global__ void maxstep_init_kernel(unsigned long long* key) { *key = dkey(CUDART_INF); }
-__global__ void maxstep_r_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
-                                 double d_scale, unsigned long long* key) {
-  double mn = CUDART_INF;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.m; i += gridDim.x * blockDim.x) {
-    if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
-    if (d) {
-      const double di = d[i] / d_scale;
-      if (di > 0) mn = fmin(mn, x[i] / di);                     // maxstep_rp, :212-225
-    } else {
-      mn = fmin(mn, x[i] > 0 ? 0.0 : -1.0 + x[i]);              // :227-240
-    }
-  }
-  mn = warp_min(mn);
-  if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
-}
+// ================================================================= max step helpers
 __device__ __forceinline__ double rp_candidate(double x, const double* d, size_t i, double d_scale) {
   if (d) {
     const double di = d[i] / d_scale;
@@ -267,82 +71,6 @@ __device__ __forceinline__ double rp_candidate(double x, const double* d, size_t
   }
   return x > 0 ? 0.0 : -1.0 + x;                                   // :227-240
 }
-__global__ void maxstep_r_all_kernel(int m, const double* __restrict__ x, const double* __restrict__ d,
-                                     double d_scale, unsigned long long* key) {
-  double mn = CUDART_INF;
-  const int m2 = m >> 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m2; i += gridDim.x * blockDim.x) {
-    const double2 xx = reinterpret_cast<const double2*>(x)[i];
-    if (d) {
-      const double2 dd = reinterpret_cast<const double2*>(d)[i];
-      const double d0 = dd.x / d_scale, d1 = dd.y / d_scale;
-      if (d0 > 0) mn = fmin(mn, xx.x / d0);
-      if (d1 > 0) mn = fmin(mn, xx.y / d1);
-    } else {
-      mn = fmin(mn, fmin(xx.x > 0 ? 0.0 : -1.0 + xx.x, xx.y > 0 ? 0.0 : -1.0 + xx.y));
-    }
-  }
-  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) mn = fmin(mn, rp_candidate(x[m - 1], d, m - 1, d_scale));
-  mn = warp_min(mn);
-  if ((threadIdx.x & 31) == 0 && mn < CUDART_INF) atomicMin(key, dkey(mn));
-}
-
-// Grid-stride over the cones; every group keeps a running minimum and the CTA issues ONE atomicMin at
-// the end (half a million same-address atomics serialise in L2 and used to be the whole kernel time).
-template <int G>
-__global__ void maxstep_q_kernel(ConeDesc c, const double* __restrict__ x, const double* __restrict__ d,
-                                 double d_scale, unsigned long long* key) {
-  __shared__ double sm[8];
-  __shared__ double smin[8];
-  const int per_block = blockDim.x / G, lid = threadIdx.x % G;
-  const double ids = d ? -1.0 / d_scale : 0.0;                    // d <- -d / d_scale
-  double best = CUDART_INF;
-  for (int qi = blockIdx.x * per_block + threadIdx.x / G; qi < c.nq; qi += gridDim.x * per_block) {
-    const int ci = c.qlist[qi], off = c.off[ci], dim = c.off[ci + 1] - off;
-    const double* xp = x + off;
-    double res;
-    if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
-      double nn = 0;
-      for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
-      nn = group_sum<G>(nn, sm);
-      const double al = sqrt(nn) - xp[0];
-      res = al < 0 ? 0.0 : -1.0 - al;
-    } else {                                                       // maxstep_soc(x, d), :242-262
-      const double* dp = d + off;
-      double xx = 0, xdr = 0;
-      for (int i = lid; i < dim; i += G) { xx += xp[i] * xp[i]; }
-      xx = group_sum<G>(xx, sm);
-      const double gam = 2 * xp[0] * xp[0] - xx;
-      const double irg = 1.0 / sqrt(gam);
-      const double d0 = dp[0] * ids;
-      for (int i = lid; i < dim; i += G) xdr += (xp[i] * irg) * (dp[i] * ids);
-      const double xd = group_sum<G>(xdr, sm);
-      const double xb0 = xp[0] * irg;
-      const double beta = 2 * xb0 * d0 - xd;
-      const double rho1 = beta * irg;
-      const double mu = (beta + d0) / (xb0 + 1);
-      double r2 = 0;
-      for (int i = lid; i < dim; i += G) {
-        if (i > 0) {
-          const double r = dp[i] * ids - mu * (xp[i] * irg);
-          r2 += r * r;
-        }
-      }
-      r2 = group_sum<G>(r2, sm);
-      const double al = sqrt(r2) * irg - rho1;
-      res = al < 0 ? CUDART_INF : 1.0 / al;
-    }
-    best = fmin(best, res);
-  }
-  // every lane of a group holds the same `best`; CTA minimum through shared memory
-  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmin(best, smin[w]);
-    if (best < CUDART_INF) atomicMin(key, dkey(best));
-  }
-}
-
 // ================================================================= scaled panel  Atil = F^-T A
 __global__ void __launch_bounds__(256)
 scale_panel_diag_kernel(const double* __restrict__ At4, double* __restrict__ Atil4, int ld,
@@ -381,29 +109,346 @@ inline int nblocks(int n, int per) {
   return b < 1 ? 1 : (b > cap ? cap : b);
 }
 
-}  // namespace
-
-#define Q_DISPATCH(kernel, ...)                                                   \
-  do {                                                                            \
-    if (c.nq > 0) {                                                               \
-      if (c.max_q_dim > 1024) {                                                   \
-        kernel<256><<<c.nq, 256, 0, st>>>(__VA_ARGS__);                           \
-      } else {                                                                    \
-        kernel<32><<<(c.nq + 7) / 8, 256, 0, st>>>(__VA_ARGS__);                  \
-      }                                                                           \
-      CIP_CHECK_LAUNCH();                                                         \
-    }                                                                             \
+// ================================================================= fused R + Q kernels
+// One launch covers every R row and every Q cone of a call (the S cones, if any, take one more launch in sdp.cu):
+// blocks [0, nbR) walk the rows that are not in Q cones (grid-stride, 16-byte vectorised when every row is an R
+// row), blocks [nbR, nbR + nbQ) take the Q cones, one cone per group of G threads.  G = 8 for small cones (up to 64
+// rows: four cones per warp, three shuffle steps per reduction, no idle lanes at dimension 33), 32 up to 1024
+// rows, 256 (one CTA per cone) above.
+template <int G>
+__device__ __forceinline__ double gsum(double v, double* sm) {
+  if (G == 8) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  return group_sum<G>(v, sm);
+}
+// cone of this group; inactive groups (beyond the last cone) keep running with dim = 0 so that the warp-wide
+// shuffles stay convergent
+template <int G>
+__device__ __forceinline__ bool q_group(const ConeDesc& c, int bq, int& ci, int& off, int& dim, int& lid) {
+  const int per_block = blockDim.x / G;
+  const int qi = bq * per_block + threadIdx.x / G;
+  lid = threadIdx.x % G;
+  ci = 0; off = 0; dim = 0;
+  if (qi >= c.nq) return false;
+  ci = c.qlist[qi];
+  off = c.off[ci];
+  dim = c.off[ci + 1] - off;
+  return true;
+}
+struct RQGrid { int nbR, nbQ, G; };
+inline RQGrid rq_grid(const ConeDesc& c) {
+  RQGrid g;
+  g.G = c.max_q_dim > 1024 ? 256 : (c.max_q_dim > 64 ? 32 : 8);
+  g.nbQ = c.nq > 0 ? (c.nq + (256 / g.G) - 1) / (256 / g.G) : 0;
+  const bool all_r = (c.nq + c.ns == 0);
+  g.nbR = all_r ? nblocks(c.m / 2 + 1, 256) : ((c.nr_rows + c.ns > 0) ? nblocks(c.m, 256) : 0);
+  return g;
+}
+#define RQ_LAUNCH(kernel, c, st, ...)                                                         \
+  do {                                                                                        \
+    const RQGrid g_ = rq_grid(c);                                                             \
+    if (g_.nbR + g_.nbQ > 0) {                                                                \
+      if (g_.G == 256) kernel<256><<<g_.nbR + g_.nbQ, 256, 0, st>>>(g_.nbR, __VA_ARGS__);     \
+      else if (g_.G == 32) kernel<32><<<g_.nbR + g_.nbQ, 256, 0, st>>>(g_.nbR, __VA_ARGS__);  \
+      else kernel<8><<<g_.nbR + g_.nbQ, 256, 0, st>>>(g_.nbR, __VA_ARGS__);                   \
+      CIP_CHECK_LAUNCH();                                                                     \
+    }                                                                                         \
   } while (0)
+
+// ---- NT scaling (nt_scaling closure, src/ConicIP.jl:589-605; nestod_soc :165-194)
+template <int G>
+__global__ void __launch_bounds__(256)
+nt_rq_kernel(int nbR, ConeDesc c, const double* __restrict__ v, const double* __restrict__ s, Scaling F, Scaling Fi,
+             double* __restrict__ lambda) {
+  __shared__ double sm[8];
+  if ((int)blockIdx.x < nbR) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nbR * blockDim.x;
+    for (int i = tid; i < c.ncones; i += nth) {               // block kinds of the R cones (Q cones: below)
+      if (c.type[i] == CIP_CONE_R) { F.kind[i] = CIP_BLK_DIAG; Fi.kind[i] = CIP_BLK_DIAG; F.D[i] = 0.0; Fi.D[i] = 0.0; }
+    }
+    if (c.nq + c.ns == 0) {                                   // every row is an R row: two rows per step, no lookups
+      const int m2 = c.m >> 1;
+      for (int i = tid; i < m2; i += nth) {
+        const double2 vv = reinterpret_cast<const double2*>(v)[i], ss = reinterpret_cast<const double2*>(s)[i];
+        const double2 f = make_double2(sqrt(ss.x / vv.x), sqrt(ss.y / vv.y));
+        reinterpret_cast<double2*>(F.a)[i] = f;
+        reinterpret_cast<double2*>(F.b)[i] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2*>(Fi.a)[i] = make_double2(1.0 / f.x, 1.0 / f.y);
+        reinterpret_cast<double2*>(Fi.b)[i] = make_double2(0.0, 0.0);
+        reinterpret_cast<double2*>(lambda)[i] = make_double2(f.x * vv.x, f.y * vv.y);
+      }
+      if ((c.m & 1) && tid == 0) {
+        const int i = c.m - 1;
+        const double f = sqrt(s[i] / v[i]);
+        F.a[i] = f; F.b[i] = 0.0; Fi.a[i] = 1.0 / f; Fi.b[i] = 0.0; lambda[i] = f * v[i];
+      }
+      return;
+    }
+    for (int i = tid; i < c.m; i += nth) {
+      const int ty = c.type[c.row_cone[i]];
+      if (ty == CIP_CONE_S) { F.a[i] = 0.0; F.b[i] = 0.0; Fi.a[i] = 0.0; Fi.b[i] = 0.0; }
+      if (ty != CIP_CONE_R) continue;
+      const double f = sqrt(s[i] / v[i]);                     // Diagonal(sqrt.(yI./xI)), src/ConicIP.jl:598
+      F.a[i] = f; F.b[i] = 0.0; Fi.a[i] = 1.0 / f; Fi.b[i] = 0.0;
+      lambda[i] = f * v[i];
+    }
+    return;
+  }
+  int ci, off, dim, lid;
+  const bool on = q_group<G>(c, blockIdx.x - nbR, ci, off, dim, lid);
+  if (G == 256 && !on) return;
+  const double* z = v + off;     // nestod_soc(z = v_I, s = s_I), src/ConicIP.jl:599
+  const double* sv = s + off;
+  double zz = 0, ss = 0;
+  for (int i = lid; i < dim; i += G) { zz += z[i] * z[i]; ss += sv[i] * sv[i]; }
+  zz = gsum<G>(zz, sm);
+  ss = gsum<G>(ss, sm);
+  const double z0 = on ? z[0] : 1.0, s0 = on ? sv[0] : 1.0;
+  const double qfz = on ? 2 * z0 * z0 - zz : 1.0;             // QF, src/ConicIP.jl:160
+  const double qfs = on ? 2 * s0 * s0 - ss : 1.0;
+  const double beta = sqrt(sqrt(qfs / qfz));                  // (QF(s)/QF(z))^(1/4)
+  // normalisation by multiplication with the reciprocals (one division per cone instead of four per
+  // element; differs from the reference's elementwise z/sqrt(QF(z)) in the last bit only)
+  const double irz = 1.0 / sqrt(qfz), irs = 1.0 / sqrt(qfs);
+  double zs = 0;
+  for (int i = lid; i < dim; i += G) zs += (z[i] * irz) * (sv[i] * irs);
+  zs = gsum<G>(zs, sm);
+  const double gamma = sqrt((1 + zs) / 2);
+  const double inv2g = 1.0 / (2.0 * gamma);
+  // w = (s + Jz)/(2 gamma); w1 += 1; w *= sqrt(2 beta)/sqrt(2 w1)
+  const double w1 = inv2g * (s0 * irs + z0 * irz) + 1.0;
+  const double scal = sqrt(2 * beta) / sqrt(2 * w1);
+  double wv = 0, bib = 0;
+  for (int i = lid; i < dim; i += G) {
+    const double zi = z[i] * irz, si = sv[i] * irs;
+    const double w = (i == 0) ? w1 * scal : (inv2g * (si - zi)) * scal;
+    const double a = (i == 0) ? -beta : beta;
+    F.a[off + i] = a;
+    F.b[off + i] = w;
+    const double ia = 1.0 / a;                   // Woodbury inverse: W = inv(A), X = W*B
+    Fi.a[off + i] = ia;
+    Fi.b[off + i] = ia * w;
+    wv += w * z[i];
+    bib += w * (ia * w);
+  }
+  wv = gsum<G>(wv, sm);
+  bib = gsum<G>(bib, sm);
+  for (int i = lid; i < dim; i += G) {                             // lambda = F*v, w recomputed (no re-read)
+    const double w = (i == 0) ? w1 * scal : (inv2g * (sv[i] * irs - z[i] * irz)) * scal;
+    lambda[off + i] = ((i == 0) ? -beta : beta) * z[i] + w * wv;
+  }
+  if (on && lid == 0) {
+    F.kind[ci] = CIP_BLK_WOODBURY; Fi.kind[ci] = CIP_BLK_WOODBURY;
+    F.D[ci] = 1.0;
+    Fi.D[ci] = 1.0 / (-1.0 - bib);               // Z = inv(-inv(D) - B'X), D = 1
+  }
+}
+
+// ---- block apply  y = M x  or, twice == 1,  y = M (M x)  (M = diag(a) + D b b' per cone, symmetric), and with
+//      `minus`: y = minus - (that).  Block*x of src/blockmatrices.jl:107-131; the pair is the F^-T F^-T v of
+//      src/kktsolvers.jl:326,328 in one pass.
+template <int G>
+__global__ void __launch_bounds__(256)
+apply_rq_kernel(int nbR, ConeDesc c, Scaling S, const double* __restrict__ x, double* __restrict__ y, int twice,
+                const double* __restrict__ minus) {
+  __shared__ double sm[8];
+  if ((int)blockIdx.x < nbR) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nbR * blockDim.x;
+    if (c.nq + c.ns == 0) {
+      const int m2 = c.m >> 1;
+      for (int i = tid; i < m2; i += nth) {
+        const double2 a = reinterpret_cast<const double2*>(S.a)[i], xx = reinterpret_cast<const double2*>(x)[i];
+        double2 r = make_double2(a.x * xx.x, a.y * xx.y);
+        if (twice) { r.x *= a.x; r.y *= a.y; }
+        if (minus) { const double2 z = reinterpret_cast<const double2*>(minus)[i]; r.x = z.x - r.x; r.y = z.y - r.y; }
+        reinterpret_cast<double2*>(y)[i] = r;
+      }
+      if ((c.m & 1) && tid == 0) {
+        const int i = c.m - 1;
+        double r = S.a[i] * x[i];
+        if (twice) r *= S.a[i];
+        y[i] = minus ? minus[i] - r : r;
+      }
+      return;
+    }
+    for (int i = tid; i < c.m; i += nth) {
+      if (c.type[c.row_cone[i]] == CIP_CONE_Q) continue;      // (S rows: a = 0; sdp_apply writes them afterwards)
+      double r = S.a[i] * x[i];
+      if (twice) r *= S.a[i];
+      y[i] = minus ? minus[i] - r : r;
+    }
+    return;
+  }
+  int ci, off, dim, lid;
+  const bool on = q_group<G>(c, blockIdx.x - nbR, ci, off, dim, lid);
+  if (G == 256 && !on) return;
+  const bool wood = on && S.kind[ci] == CIP_BLK_WOODBURY;
+  const double D = wood ? S.D[ci] : 0.0;
+  double bx = 0;
+  for (int i = lid; i < dim; i += G) bx += S.b[off + i] * x[off + i];
+  bx = gsum<G>(bx, sm) * D;
+  if (!twice) {
+    for (int i = lid; i < dim; i += G) {
+      const double r = S.a[off + i] * x[off + i] + S.b[off + i] * bx;     // A*x + B*(D*(B'x))
+      y[off + i] = minus ? minus[off + i] - r : r;
+    }
+    return;
+  }
+  double bt = 0;                                                           // b' t with t = M x
+  for (int i = lid; i < dim; i += G) bt += S.b[off + i] * (S.a[off + i] * x[off + i] + S.b[off + i] * bx);
+  bt = gsum<G>(bt, sm) * D;
+  for (int i = lid; i < dim; i += G) {
+    const double tt = S.a[off + i] * x[off + i] + S.b[off + i] * bx;
+    const double r = S.a[off + i] * tt + S.b[off + i] * bt;
+    y[off + i] = minus ? minus[off + i] - r : r;
+  }
+}
+
+// ---- Jordan product / division (cone_prod!, cone_div!: src/ConicIP.jl:622-665, :305-345)
+template <int G>
+__global__ void __launch_bounds__(256)
+prod_rq_kernel(int nbR, ConeDesc c, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o,
+               int divide) {
+  __shared__ double sm[8];
+  if ((int)blockIdx.x < nbR) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nbR * blockDim.x;
+    if (c.nq + c.ns == 0) {
+      const int m2 = c.m >> 1;
+      for (int i = tid; i < m2; i += nth) {
+        const double2 a = reinterpret_cast<const double2*>(x)[i], b = reinterpret_cast<const double2*>(y)[i];
+        reinterpret_cast<double2*>(o)[i] = divide ? make_double2(a.x / b.x, a.y / b.y) : make_double2(a.x * b.x, a.y * b.y);
+      }
+      if ((c.m & 1) && tid == 0) o[c.m - 1] = divide ? x[c.m - 1] / y[c.m - 1] : x[c.m - 1] * y[c.m - 1];
+      return;
+    }
+    for (int i = tid; i < c.m; i += nth) {
+      if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+      o[i] = divide ? x[i] / y[i] : x[i] * y[i];             // drp! / xrp!, src/ConicIP.jl:305-315
+    }
+    return;
+  }
+  int ci, off, dim, lid;
+  const bool on = q_group<G>(c, blockIdx.x - nbR, ci, off, dim, lid);
+  if (G == 256 && !on) return;
+  const double* xp = x + off;
+  const double* yp = y + off;
+  if (!divide) {                                                // xsoc!, :340-345
+    double d = 0;
+    for (int i = lid; i < dim; i += G) d += xp[i] * yp[i];
+    d = gsum<G>(d, sm);
+    const double x0 = on ? xp[0] : 0.0, y0 = on ? yp[0] : 0.0;
+    for (int i = lid; i < dim; i += G) o[off + i] = (i == 0) ? d : x0 * yp[i] + y0 * xp[i];
+    return;
+  }
+  // o = arrow(y)^-1 x   (dsoc!(y = x_arg, x = y_arg, o), src/ConicIP.jl:317-338)
+  double ybyb = 0, ybxb = 0;
+  for (int i = lid; i < dim; i += G) {
+    if (i > 0) { ybyb += yp[i] * yp[i]; ybxb += yp[i] * xp[i]; }
+  }
+  ybyb = gsum<G>(ybyb, sm);
+  ybxb = gsum<G>(ybxb, sm);
+  const double y1 = on ? yp[0] : 1.0, x1 = on ? xp[0] : 0.0;
+  const double alpha = y1 * y1 - ybyb;
+  const double b1 = (-x1 / alpha) + ybxb / (y1 * alpha);
+  const double b2 = 1.0 / y1;
+  for (int i = lid; i < dim; i += G) o[off + i] = (i == 0) ? (y1 * x1 - ybxb) / alpha : yp[i] * b1 + xp[i] * b2;
+}
+
+// ---- max step (maxstep closure src/ConicIP.jl:571-587; maxstep_rp :212-240, maxstep_soc :242-270).  *key is preset
+//      to all ones ("nothing seen" = +Inf) by a memset; every CTA issues at most one atomicMin on the
+//      order-preserving integer image of its minimum (exact and order independent).
+template <int G>
+__global__ void __launch_bounds__(256)
+maxstep_rq_kernel(int nbR, ConeDesc c, const double* __restrict__ x, const double* __restrict__ d, double d_scale,
+                  unsigned long long* key) {
+  __shared__ double sm[8];
+  __shared__ double smin[8];
+  double best = CUDART_INF;
+  if ((int)blockIdx.x < nbR) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = nbR * blockDim.x;
+    if (c.nq + c.ns == 0) {
+      const int m2 = c.m >> 1;
+      for (int i = tid; i < m2; i += nth) {
+        const double2 xx = reinterpret_cast<const double2*>(x)[i];
+        if (d) {
+          const double2 dd = reinterpret_cast<const double2*>(d)[i];
+          const double d0 = dd.x / d_scale, d1 = dd.y / d_scale;
+          if (d0 > 0) best = fmin(best, xx.x / d0);
+          if (d1 > 0) best = fmin(best, xx.y / d1);
+        } else {
+          best = fmin(best, fmin(xx.x > 0 ? 0.0 : -1.0 + xx.x, xx.y > 0 ? 0.0 : -1.0 + xx.y));
+        }
+      }
+      if ((c.m & 1) && tid == 0) best = fmin(best, rp_candidate(x[c.m - 1], d, c.m - 1, d_scale));
+    } else {
+      for (int i = tid; i < c.m; i += nth) {
+        if (c.type[c.row_cone[i]] != CIP_CONE_R) continue;
+        best = fmin(best, rp_candidate(x[i], d, i, d_scale));
+      }
+    }
+    best = warp_min(best);
+  } else {
+    const int per_block = blockDim.x / G, lid = threadIdx.x % G;
+    const double ids = d ? -1.0 / d_scale : 0.0;                    // d <- -d / d_scale
+    const int qi = (blockIdx.x - nbR) * per_block + threadIdx.x / G;
+    const bool on = qi < c.nq;
+    if (G == 256 && !on) return;
+    const int ci = on ? c.qlist[qi] : 0, off = on ? c.off[ci] : 0, dim = on ? c.off[ci + 1] - off : 0;
+    const double* xp = x + off;
+    double res;
+    if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
+      double nn = 0;
+      for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
+      nn = gsum<G>(nn, sm);
+      const double al = sqrt(nn) - (on ? xp[0] : 1.0);
+      res = al < 0 ? 0.0 : -1.0 - al;
+    } else {                                                       // maxstep_soc(x, d), :242-262
+      const double* dp = d + off;
+      double xx = 0, xdr = 0;
+      for (int i = lid; i < dim; i += G) { xx += xp[i] * xp[i]; }
+      xx = gsum<G>(xx, sm);
+      const double x0 = on ? xp[0] : 1.0;
+      const double gam = on ? 2 * x0 * x0 - xx : 1.0;
+      const double irg = 1.0 / sqrt(gam);
+      const double d0 = on ? dp[0] * ids : 0.0;
+      for (int i = lid; i < dim; i += G) xdr += (xp[i] * irg) * (dp[i] * ids);
+      const double xd = gsum<G>(xdr, sm);
+      const double xb0 = x0 * irg;
+      const double beta = 2 * xb0 * d0 - xd;
+      const double rho1 = beta * irg;
+      const double mu = (beta + d0) / (xb0 + 1);
+      double r2 = 0;
+      for (int i = lid; i < dim; i += G) {
+        if (i > 0) {
+          const double r = dp[i] * ids - mu * (xp[i] * irg);
+          r2 += r * r;
+        }
+      }
+      r2 = gsum<G>(r2, sm);
+      const double al = sqrt(r2) * irg - rho1;
+      res = al < 0 ? CUDART_INF : 1.0 / al;
+    }
+    best = on ? res : CUDART_INF;
+    if (G == 8) best = warp_min(best);                             // four cones per warp
+  }
+  // CTA minimum through shared memory, one atomic per CTA
+  if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmin(best, smin[w]);
+    if (best < CUDART_INF) atomicMin(key, dkey(best));
+  }
+}
+
+}  // namespace
 
 int cone_nt_scaling(const ConeDesc& c, const double* v, const double* s, Scaling F, Scaling Fi, double* lambda,
                     int* info, cudaStream_t st) {
   if (c.m == 0) return 0;
-  nt_kind_kernel<<<(c.ncones + 255) / 256, 256, 0, st>>>(c, F, Fi);
-  CIP_CHECK_LAUNCH();
-  if (c.nq + c.ns == 0) nt_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, v, s, F, Fi, lambda);
-  else if (c.nr_rows + c.ns > 0) nt_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, v, s, F, Fi, lambda);
-  CIP_CHECK_LAUNCH();
-  Q_DISPATCH(nt_q_kernel, c, v, s, F, Fi, lambda);
+  RQ_LAUNCH(nt_rq_kernel, c, st, c, v, s, F, Fi, lambda);
   CIP_TRY(sdp_nt_scaling(c, F, Fi, v, s, lambda, info, st));
   return 0;
 }
@@ -423,33 +468,38 @@ int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, c
   if (c.m == 0) return 0;
   const bool inv = (op == CIP_OP_FINVT || op == CIP_OP_FINV);
   const Scaling& S = inv ? Fi : F;           // R / Q blocks are symmetric: F' = F
-  apply_diag_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c.m, S.a, x, y);
-  CIP_CHECK_LAUNCH();
-  if (c.nq + c.ns > 0) {   // only non-R cones can carry a Woodbury block
-    apply_wood_kernel<<<(c.ncones + 7) / 8, 256, 0, st>>>(c, S, x, y);
-    CIP_CHECK_LAUNCH();
-  }
+  RQ_LAUNCH(apply_rq_kernel, c, st, c, S, x, y, 0, (const double*)nullptr);
   // VecCongurance blocks: F -> R, F' -> R', inv(F) -> inv(R), inv(F)' -> inv(R)'
   CIP_TRY(sdp_apply(c, F, inv ? 1 : 0, (op == CIP_OP_FT || op == CIP_OP_FINVT) ? 1 : 0, x, y, st));
   return 0;
 }
 
+// y = inv(F) inv(F)' x  (= inv(F'F) x), optionally y = minus - that: the two block applies of src/kktsolvers.jl:326
+// and :328 (and the subtraction of :328) in one launch for the R / Q cones; `tmp` (m doubles) is only used when
+// there are S cones.
+int cone_apply_invsq(const ConeDesc& c, const Scaling& F, const Scaling& Fi, const double* x, double* y,
+                     const double* minus, double* tmp, cudaStream_t st) {
+  if (c.m == 0) return 0;
+  RQ_LAUNCH(apply_rq_kernel, c, st, c, Fi, x, y, 1, minus);
+  if (c.ns > 0) {
+    // VecCongurance blocks are not symmetric: inv(R)' first, then inv(R), on the S rows only
+    CIP_TRY(sdp_apply(c, F, 1, 1, x, tmp, st));
+    CIP_TRY(sdp_apply(c, F, 1, 0, tmp, y, st));
+    if (minus) CIP_TRY(sdp_rows_rsub(c, minus, y, st));
+  }
+  return 0;
+}
+
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
-  if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 0);
-  else if (c.nr_rows > 0) prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 0);
-  CIP_CHECK_LAUNCH();
-  Q_DISPATCH(prod_q_kernel, c, x, y, o);
+  RQ_LAUNCH(prod_rq_kernel, c, st, c, x, y, o, 0);
   CIP_TRY(sdp_prod_div(c, x, y, o, 0, st));
   return 0;
 }
 
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st) {
   if (c.m == 0) return 0;
-  if (c.nq + c.ns == 0) prod_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, y, o, 1);
-  else if (c.nr_rows > 0) prod_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, y, o, 1);
-  CIP_CHECK_LAUNCH();
-  Q_DISPATCH(div_q_kernel, c, x, y, o);
+  RQ_LAUNCH(prod_rq_kernel, c, st, c, x, y, o, 1);
   CIP_TRY(sdp_prod_div(c, x, y, o, 1, st));
   return 0;
 }
@@ -458,17 +508,9 @@ int cone_maxstep(const ConeDesc& c, const double* x, const double* d, double d_s
                  int npartial, double* result, cudaStream_t st) {
   (void)partial; (void)npartial;
   unsigned long long* key = reinterpret_cast<unsigned long long*>(result);
-  maxstep_init_kernel<<<1, 1, 0, st>>>(key);
-  CIP_CHECK_LAUNCH();
+  CIP_CUDA(cudaMemsetAsync(key, 0xFF, sizeof(unsigned long long), st));      // "nothing seen": decoded as +Inf
   if (c.m == 0) return 0;
-  if (c.nq + c.ns == 0) maxstep_r_all_kernel<<<nblocks(c.m / 2 + 1, 256), 256, 0, st>>>(c.m, x, d, d_scale, key);
-  else if (c.nr_rows > 0) maxstep_r_kernel<<<nblocks(c.m, 256), 256, 0, st>>>(c, x, d, d_scale, key);
-  CIP_CHECK_LAUNCH();
-  if (c.nq > 0) {
-    if (c.max_q_dim > 1024) maxstep_q_kernel<256><<<std::min(c.nq, sm_count() * 8), 256, 0, st>>>(c, x, d, d_scale, key);
-    else maxstep_q_kernel<32><<<std::min((c.nq + 7) / 8, sm_count() * 8), 256, 0, st>>>(c, x, d, d_scale, key);
-    CIP_CHECK_LAUNCH();
-  }
+  RQ_LAUNCH(maxstep_rq_kernel, c, st, c, x, d, d_scale, key);
   CIP_TRY(sdp_maxstep(c, x, d, d_scale, key, st));
   return 0;
 }

@@ -103,6 +103,30 @@ int stage_out(cip_engine* h, double* dst, const double* src, size_t n) {
   if (!is_device_ptr(dst)) h->need_sync = true;
   return 0;
 }
+// Vector arguments that already live in this device's memory (16-byte aligned) are used where they are: the
+// kernels below index strictly inside [0, n), so no zero-padded private copy is needed.  Host memory, memory of
+// another GPU and odd alignments go through the internal staging buffer as before.  `padded`: the consumer reads
+// whole quads (the k-major mat-vec), so a direct pointer is only allowed when n is a multiple of 4.
+bool direct_ok(const cip_engine* h, const void* p, size_t n, bool padded = false) {
+  if (!p || (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
+  if (padded && (n & 3) != 0) return false;
+  return kernel_readable(p, h->device);
+}
+int vec_in(cip_engine* h, double* stage, const double* src, size_t n, const double** use, bool padded = false) {
+  if (n == 0) { *use = stage; return 0; }
+  if (direct_ok(h, src, n, padded)) { *use = src; return 0; }
+  *use = stage;
+  return stage_in(h, stage, src, n);
+}
+// where a result should be produced: the caller's buffer itself, or the staging buffer (copied out afterwards)
+double* vec_out(cip_engine* h, double* stage, double* dst, size_t n) {
+  return (n > 0 && direct_ok(h, dst, n)) ? dst : stage;
+}
+int vec_out_done(cip_engine* h, double* dst, const double* produced, size_t n) {
+  if (n == 0 || !dst || produced == dst) return 0;
+  return stage_out(h, dst, produced, n);
+}
+
 int finish(cip_engine* h) {
   if (h->need_sync || h->always_sync) {
     CIP_CUDA(cudaStreamSynchronize(h->stream));
@@ -835,12 +859,14 @@ int cip_factor(cip_handle h, const int* kind, const double* fa, const double* fb
 int cip_nt_scaling(cip_handle h, const double* v, const double* s, double* lambda_out) {
   CIP_TRY(check(h));
   if (h->multi) return multi_nt_scaling(h, v, s, lambda_out, 0);
-  CIP_TRY(stage_in(h, h->mv[7], v, h->m));
-  CIP_TRY(stage_in(h, h->mv[8], s, h->m));
+  const double *vp, *sp;
+  CIP_TRY(vec_in(h, h->mv[7], v, h->m, &vp));
+  CIP_TRY(vec_in(h, h->mv[8], s, h->m, &sp));
+  double* lp = vec_out(h, h->mv[9], lambda_out, h->m);
   if (h->cd.ns > 0) CIP_CUDA(cudaMemsetAsync(h->info + 2, 0, sizeof(int), h->stream));
-  CIP_TRY(cone_nt_scaling(h->cd, h->mv[7], h->mv[8], h->F, h->Fi, h->mv[9], h->info + 2, h->stream));
+  CIP_TRY(cone_nt_scaling(h->cd, vp, sp, h->F, h->Fi, lp, h->info + 2, h->stream));
   h->have_scaling = true;
-  CIP_TRY(stage_out(h, lambda_out, h->mv[9], h->m));
+  CIP_TRY(vec_out_done(h, lambda_out, lp, h->m));
   if (h->cd.ns > 0) {
     // an S-cone iterate that is not positive definite has no NT scaling (PosDefException in the reference,
     // src/ConicIP.jl:201-202): report it as a numerical failure (> 0) instead of handing out garbage
@@ -884,25 +910,29 @@ int cip_apply(cip_handle h, int op, const double* x, double* y) {
   CIP_TRY(check(h));
   if (h->multi) return multi_apply(h, op, x, y);
   if (!h->have_scaling) { set_error("no scaling set"); return -1; }
-  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
   if (op < CIP_OP_F || op > CIP_OP_FINV) { set_error("cip_apply: bad op %d", op); return -1; }
-  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, op, h->mv[7], h->mv[8], h->stream));
-  CIP_TRY(stage_out(h, y, h->mv[8], h->m));
+  const double* xp;
+  CIP_TRY(vec_in(h, h->mv[7], x, h->m, &xp));
+  double* yp = (y != x) ? vec_out(h, h->mv[8], y, h->m) : h->mv[8];
+  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, op, xp, yp, h->stream));
+  CIP_TRY(vec_out_done(h, y, yp, h->m));
   return finish(h);
 }
 
 int cip_maxstep(cip_handle h, const double* x, const double* d, double d_scale, double* alpha_out) {
   CIP_TRY(check(h));
   if (h->multi) return multi_maxstep(h, x, d, d_scale, alpha_out);
-  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
-  if (d) CIP_TRY(stage_in(h, h->mv[8], d, h->m));
-  CIP_TRY(cone_maxstep(h->cd, h->mv[7], d ? h->mv[8] : nullptr, d_scale, nullptr, 0, h->scalar, h->stream));
+  const double *xp, *dp = nullptr;
+  CIP_TRY(vec_in(h, h->mv[7], x, h->m, &xp));
+  if (d) CIP_TRY(vec_in(h, h->mv[8], d, h->m, &dp));
+  CIP_TRY(cone_maxstep(h->cd, xp, dp, d_scale, nullptr, 0, h->scalar, h->stream));
   unsigned long long key = 0;
   CIP_CUDA(cudaMemcpyAsync(&key, h->scalar, 8, cudaMemcpyDeviceToHost, h->stream));
   CIP_CUDA(cudaStreamSynchronize(h->stream));
   const unsigned long long u = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
   double r;
   memcpy(&r, &u, 8);
+  if (key == ~0ull) r = INFINITY;               // the preset value: no cone bounded the step
   *alpha_out = r;
   return 0;
 }
@@ -910,20 +940,24 @@ int cip_maxstep(cip_handle h, const double* x, const double* d, double d_scale, 
 int cip_cone_prod(cip_handle h, const double* x, const double* y, double* o) {
   CIP_TRY(check(h));
   if (h->multi) return multi_prod_div(h, x, y, o, 0);
-  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
-  CIP_TRY(stage_in(h, h->mv[8], y, h->m));
-  CIP_TRY(cone_prod(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
-  CIP_TRY(stage_out(h, o, h->mv[9], h->m));
+  const double *xp, *yp;
+  CIP_TRY(vec_in(h, h->mv[7], x, h->m, &xp));
+  CIP_TRY(vec_in(h, h->mv[8], y, h->m, &yp));
+  double* op_ = (o != x && o != y) ? vec_out(h, h->mv[9], o, h->m) : h->mv[9];
+  CIP_TRY(cone_prod(h->cd, xp, yp, op_, h->stream));
+  CIP_TRY(vec_out_done(h, o, op_, h->m));
   return finish(h);
 }
 
 int cip_cone_div(cip_handle h, const double* x, const double* y, double* o) {
   CIP_TRY(check(h));
   if (h->multi) return multi_prod_div(h, x, y, o, 1);
-  CIP_TRY(stage_in(h, h->mv[7], x, h->m));
-  CIP_TRY(stage_in(h, h->mv[8], y, h->m));
-  CIP_TRY(cone_div(h->cd, h->mv[7], h->mv[8], h->mv[9], h->stream));
-  CIP_TRY(stage_out(h, o, h->mv[9], h->m));
+  const double *xp, *yp;
+  CIP_TRY(vec_in(h, h->mv[7], x, h->m, &xp));
+  CIP_TRY(vec_in(h, h->mv[8], y, h->m, &yp));
+  double* op_ = (o != x && o != y) ? vec_out(h, h->mv[9], o, h->m) : h->mv[9];
+  CIP_TRY(cone_div(h->cd, xp, yp, op_, h->stream));
+  CIP_TRY(vec_out_done(h, o, op_, h->m));
   return finish(h);
 }
 
@@ -934,22 +968,24 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   if (!h->have_factor) { set_error("cip_solve before cip_factor"); return -1; }
   cudaStream_t s = h->stream;
   CIP_CUDA(cudaEventRecord(h->ev[6], s));
-  CIP_TRY(stage_in(h, h->nv[0], ry, h->n));
+  const double *ryp, *rvp;
+  CIP_TRY(vec_in(h, h->nv[0], ry, h->n, &ryp));
   if (h->p) CIP_TRY(stage_in(h, h->pv[0], rw, h->p));
-  CIP_TRY(stage_in(h, h->mv[0], rv, h->m));
+  CIP_TRY(vec_in(h, h->mv[0], rv, h->m, &rvp));
+  double* dvp = (dv != rv) ? vec_out(h, h->mv[5], dv, h->m) : h->mv[5];
   // t1 = F^-T (F^-T v)                                   (src/kktsolvers.jl:326)
   // (= inv(F'F) v; for the non-symmetric VecCongurance blocks this is inv(F) inv(F)' v, which is
   //  what the 3x3 system requires -- the reference's pivot is only right for symmetric F)
-  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINVT, h->mv[0], h->mv[1], s));
-  CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINV, h->mv[1], h->mv[2], s));
-  // rhs = y + A' t1                                      (:327)
-  if (h->m) {
-    CIP_TRY(q4_mv_rows(h->nv[1], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->partial, h->partial_cap, s));
+  CIP_TRY(cone_apply_invsq(h->cd, h->F, h->Fi, rvp, h->mv[2], nullptr, h->mv[1], s));
+  // rhs = y + A' t1                                      (:327); single GPU: y is added in the mat-vec's second pass
+  if (h->m && !h->comm) {
+    CIP_TRY(q4_mv_rows(h->nv[2], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->partial, h->partial_cap, s, ryp));
   } else {
-    CIP_TRY(fill_zero(h->nv[1], h->n, s));
+    if (h->m) CIP_TRY(q4_mv_rows(h->nv[1], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->partial, h->partial_cap, s));
+    else CIP_TRY(fill_zero(h->nv[1], h->n, s));
+    CIP_TRY(allreduce(h, h->nv[1], h->n));
+    CIP_TRY(vec_axpby(h->nv[2], 1.0, ryp, 1.0, h->nv[1], h->n, s));
   }
-  CIP_TRY(allreduce(h, h->nv[1], h->n));
-  CIP_TRY(vec_axpby(h->nv[2], 1.0, h->nv[0], 1.0, h->nv[1], h->n, s));
   if (h->aug_rows > 0) {        // rhs += rho G' rw  (same (dy, dw) as the unaugmented system)
     CIP_TRY(q4_mv_k(h->nv[4], h->G4, h->p_pad, h->p, h->n, h->pv[0], s));
     CIP_TRY(vec_axpby(h->nv[2], 1.0, h->nv[2], h->aug_rho, h->nv[4], h->n, s));
@@ -968,14 +1004,12 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
   // dv = t1 - F^-T F^-T (A dy)                           (:328)
   if (h->m) {
     CIP_TRY(q4_mv_k(h->mv[3], h->At4, h->n_pad, h->n, h->m, h->nv[5], s));
-    CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINVT, h->mv[3], h->mv[1], s));
-    CIP_TRY(cone_apply(h->cd, h->F, h->Fi, CIP_OP_FINV, h->mv[1], h->mv[4], s));
-    CIP_TRY(vec_axpby(h->mv[5], 1.0, h->mv[2], -1.0, h->mv[4], h->m, s));
+    CIP_TRY(cone_apply_invsq(h->cd, h->F, h->Fi, h->mv[3], dvp, h->mv[2], h->mv[1], s));   // t1 - (F'F)^-1 (A dy)
   }
   CIP_CUDA(cudaEventRecord(h->ev[7], s));
   CIP_TRY(stage_out(h, dy, h->nv[5], h->n));
   if (h->p) CIP_TRY(stage_out(h, dw, h->pv[4], h->p));
-  CIP_TRY(stage_out(h, dv, h->mv[5], h->m));
+  CIP_TRY(vec_out_done(h, dv, dvp, h->m));
   h->st.solves++;
   if (h->need_sync || h->always_sync) {
     // the call synchronises anyway: also read the give-up flag of the persistent sweeps (a hand-off that never
@@ -1013,15 +1047,19 @@ int cip_mul_A(cip_handle h, int trans, const double* x, double* y) {
   if (h->multi) return multi_mul_A(h, trans, x, y);
   cudaStream_t s = h->stream;
   if (!trans) {
-    CIP_TRY(stage_in(h, h->nv[6], x, h->n));
-    CIP_TRY(q4_mv_k(h->mv[6], h->At4, h->n_pad, h->n, h->m, h->nv[6], s));
-    CIP_TRY(stage_out(h, y, h->mv[6], h->m));
+    const double* xp;
+    CIP_TRY(vec_in(h, h->nv[6], x, h->n, &xp));
+    double* yp = vec_out(h, h->mv[6], y, h->m);
+    CIP_TRY(q4_mv_k(yp, h->At4, h->n_pad, h->n, h->m, xp, s));
+    CIP_TRY(vec_out_done(h, y, yp, h->m));
   } else {
-    CIP_TRY(stage_in(h, h->mv[6], x, h->m));
-    if (h->m) CIP_TRY(q4_mv_rows(h->nv[6], h->At4, h->n_pad, h->n, h->m, h->mv[6], h->partial, h->partial_cap, s));
-    else CIP_TRY(fill_zero(h->nv[6], h->n, s));
-    CIP_TRY(allreduce(h, h->nv[6], h->n));
-    CIP_TRY(stage_out(h, y, h->nv[6], h->n));
+    const double* xp;
+    CIP_TRY(vec_in(h, h->mv[6], x, h->m, &xp, /*padded=*/true));
+    double* yp = vec_out(h, h->nv[6], y, h->n);
+    if (h->m) CIP_TRY(q4_mv_rows(yp, h->At4, h->n_pad, h->n, h->m, xp, h->partial, h->partial_cap, s));
+    else CIP_TRY(fill_zero(yp, h->n, s));
+    CIP_TRY(allreduce(h, yp, h->n));
+    CIP_TRY(vec_out_done(h, y, yp, h->n));
   }
   return finish(h);
 }
@@ -1053,9 +1091,11 @@ int cip_mul_Q(cip_handle h, const double* x, double* y) {
   CIP_TRY(check(h));
   if (h->multi) return multi_mul_GQ(h, 1, 0, x, y);
   cudaStream_t s = h->stream;
-  CIP_TRY(stage_in(h, h->nv[6], x, h->n));
-  CIP_TRY(q4_mv_rows(h->nv[7], h->Qq4, h->n_pad, h->n, h->n, h->nv[6], h->partial, h->partial_cap, s));
-  CIP_TRY(stage_out(h, y, h->nv[7], h->n));
+  const double* xp;
+  CIP_TRY(vec_in(h, h->nv[6], x, h->n, &xp, /*padded=*/true));
+  double* yp = (y != x) ? vec_out(h, h->nv[7], y, h->n) : h->nv[7];
+  CIP_TRY(q4_mv_rows(yp, h->Qq4, h->n_pad, h->n, h->n, xp, h->partial, h->partial_cap, s));
+  CIP_TRY(vec_out_done(h, y, yp, h->n));
   return finish(h);
 }
 

@@ -30,8 +30,9 @@ int fill_zero(double* p, size_t n, cudaStream_t s);
 // ---------------------------------------------------------------- mat-vec on Q4 (matvec.cu)
 // out[r] (+)= sum_k X[r,k] v[k]   (thread per row; deterministic two-pass over k splits)
 // v must be readable and finite up to round_up(K,4).
+// `add` (optional, R doubles) is added in the second pass: out = add + X v
 int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double* v, double* partial,
-               int partial_capacity, cudaStream_t s);
+               int partial_capacity, cudaStream_t s, const double* add = nullptr);
 // out[k] = sum_r X[r,k] u[r]      (warp per k-quad)
 int q4_mv_k(double* out, const double* X, int ld, int R, int K, const double* u, cudaStream_t s);
 
@@ -66,6 +67,9 @@ int cone_invert_scaling(const ConeDesc& c, Scaling F, Scaling Fi, cudaStream_t s
 // y = op(F) x with op in CIP_OP_{F,FT,FINVT,FINV}; Fi is the precomputed inverse of the diag/Woodbury part
 int cone_apply(const ConeDesc& c, const Scaling& F, const Scaling& Fi, int op, const double* x, double* y,
                cudaStream_t st);
+// y = inv(F) inv(F)' x, or y = minus - inv(F) inv(F)' x  (src/kktsolvers.jl:326,328); tmp: m doubles, S cones only
+int cone_apply_invsq(const ConeDesc& c, const Scaling& F, const Scaling& Fi, const double* x, double* y,
+                     const double* minus, double* tmp, cudaStream_t st);
 int cone_prod(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
 int cone_div(const ConeDesc& c, const double* x, const double* y, double* o, cudaStream_t st);
 // result (device scalar) = min over cones; d == nullptr -> `nothing` variant
@@ -82,6 +86,8 @@ int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, c
 int sdp_nt_scaling(const ConeDesc& c, Scaling F, Scaling Fi, const double* v, const double* s, double* lambda,
                    int* info, cudaStream_t st);
 int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st);
+// y = minus - y on the rows of the S cones
+int sdp_rows_rsub(const ConeDesc& c, const double* minus, double* y, cudaStream_t st);
 int sdp_prod_div(const ConeDesc& c, const double* x, const double* y, double* o, int divide, cudaStream_t st);
 int sdp_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, unsigned long long* key,
                 cudaStream_t st);

@@ -136,12 +136,12 @@ mv_rows_kernel(double* __restrict__ partial, const double* __restrict__ X, int l
 }
 
 __global__ void mv_rows_reduce_kernel(double* __restrict__ out, const double* __restrict__ partial, int R,
-                                      int nsplit) {
+                                      int nsplit, const double* __restrict__ add) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   double s = 0;
   for (int i = 0; i < nsplit; ++i) s += partial[(size_t)i * R + r];
-  out[r] = s;
+  out[r] = add ? add[r] + s : s;
 }
 
 // out[4kq..4kq+3] = sum_r X[r, 4kq..] u[r]; one warp per k-quad
@@ -247,7 +247,7 @@ int fill_zero(double* p, size_t n, cudaStream_t s) {
 }
 
 int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double* v, double* partial,
-               int partial_capacity, cudaStream_t s) {
+               int partial_capacity, cudaStream_t s, const double* add) {
   if (R <= 0) return 0;
   const int Kq = (K + 3) / 4;  // v must be readable (zero-padded) up to 4*Kq
   const int rblocks = (R + 127) / 128;
@@ -263,7 +263,7 @@ int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double*
   dim3 grid(rblocks, nsplit);
   mv_rows_kernel<<<grid, 128, 0, s>>>(partial, X, ld, R, Kq, v, per, K);
   CIP_CHECK_LAUNCH();
-  mv_rows_reduce_kernel<<<(R + 255) / 256, 256, 0, s>>>(out, partial, R, nsplit);
+  mv_rows_reduce_kernel<<<(R + 255) / 256, 256, 0, s>>>(out, partial, R, nsplit, add);
   CIP_CHECK_LAUNCH();
   return 0;
 }

@@ -507,6 +507,19 @@ int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st) {
   CIP_CHECK_LAUNCH();
   return 0;
 }
+namespace {
+__global__ void sdp_rows_rsub_kernel(SDesc d, const double* __restrict__ minus, double* __restrict__ y) {
+  const int si = blockIdx.x, ci = d.slist[si];
+  const int k = d.sord[si], off = d.off[ci], dim = k * (k + 1) / 2;
+  for (int e = threadIdx.x; e < dim; e += blockDim.x) y[off + e] = minus[off + e] - y[off + e];
+}
+}  // namespace
+int sdp_rows_rsub(const ConeDesc& c, const double* minus, double* y, cudaStream_t st) {
+  if (c.ns == 0) return 0;
+  sdp_rows_rsub_kernel<<<c.ns, NT, 0, st>>>(sdesc(c), minus, y);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
 int sdp_prod_div(const ConeDesc& c, const double* x, const double* y, double* o, int divide, cudaStream_t st) {
   if (c.ns == 0) return 0;
   CIP_TRY(set_attrs());

@@ -19,7 +19,7 @@ CONE_CODE = {"R": CONE_R, "Q": CONE_Q, "S": CONE_S}
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("device", C.c_int), ("reg_delta", C.c_double),
                 ("reg_eps_G", C.c_double), ("q_kind", C.c_int), ("verbose", C.c_int), ("dist_chol", C.c_int), ("aug_rho", C.c_double),
-                ("ngpus", C.c_int)]
+                ("ngpus", C.c_int), ("fold_scaling", C.c_int)]
 
 
 class Stats(C.Structure):

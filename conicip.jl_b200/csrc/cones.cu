@@ -405,6 +405,39 @@ maxstep_rq_kernel(int nbR, ConeDesc c, const double* __restrict__ x, const doubl
       nn = gsum<G>(nn, sm);
       const double al = sqrt(nn) - (on ? xp[0] : 1.0);
       res = al < 0 ? 0.0 : -1.0 - al;
+    } else if (G == 8) {                                           // maxstep_soc(x, d), :242-262; cone <= 64 rows:
+      const double* dp = d + off;                                  // one pass over memory, x and d stay in registers
+      double xr[8], dr[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = lid + 8 * e;
+        xr[e] = i < dim ? xp[i] : 0.0;
+        dr[e] = i < dim ? dp[i] * ids : 0.0;
+      }
+      double xx = 0, xdr = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xx += xr[e] * xr[e];
+      xx = gsum<G>(xx, sm);
+      const double x0 = __shfl_sync(0xffffffffu, xr[0], threadIdx.x & 24);      // element 0 lives in lane 0 of the group
+      const double d0 = __shfl_sync(0xffffffffu, dr[0], threadIdx.x & 24);
+      const double gam = on ? 2 * x0 * x0 - xx : 1.0;
+      const double irg = 1.0 / sqrt(gam);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xdr += (xr[e] * irg) * dr[e];
+      const double xd = gsum<G>(xdr, sm);
+      const double xb0 = x0 * irg;
+      const double beta = 2 * xb0 * d0 - xd;
+      const double rho1 = beta * irg;
+      const double mu = (beta + d0) / (xb0 + 1);
+      double r2 = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const double r = dr[e] - mu * (xr[e] * irg);
+        if (lid + 8 * e > 0 && lid + 8 * e < dim) r2 += r * r;
+      }
+      r2 = gsum<G>(r2, sm);
+      const double al = sqrt(r2) * irg - rho1;
+      res = al < 0 ? CUDART_INF : 1.0 / al;
     } else {                                                       // maxstep_soc(x, d), :242-262
       const double* dp = d + off;
       double xx = 0, xdr = 0;

@@ -135,6 +135,8 @@ int finish(cip_engine* h) {
   return 0;
 }
 
+size_t opts_size(const cip_options* o) { return o ? (size_t)o->struct_size : 0; }
+
 int check(cip_handle h) {
   if (!h) {
     set_error("null handle");
@@ -254,8 +256,10 @@ int form_H_sharded(cip_engine* h, const double* cin, int k_rows) {
     a.nk = k_rows / 32;
     a.Cin = cin; a.Cout = h->H4; a.Ctm = h->Hp; a.ldc = h->n_pad; a.alpha = 1.0;
     a.tile_begin = (int)t0; a.tile_count = (int)(ends[i] - t0);
+    if (h->fold) a.kscale = h->Fi.a;
     if (i == nr - 1) { a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES; }     // split-K only for the very last wave
-    CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, st));
+    const GemmOperand& op = h->fold ? h->mapAt : h->mapAtil;
+    CIP_TRY(launch_gemm_nt(op, op, a, st));
     CIP_CUDA(cudaEventRecord(h->evc[i], st));
     CIP_CUDA(cudaStreamWaitEvent(h->cs, h->evc[i], 0));
     double* seg = h->Hp + (size_t)t0 * TILE * TILE;
@@ -284,7 +288,7 @@ int form_H(cip_engine* h) {
   }
   cudaStream_t s = h->stream;
   CIP_CUDA(cudaEventRecord(h->ev[0], s));
-  if (h->m_pad > 0) CIP_TRY(cone_scale_panel(h->cd, h->Fi, h->At4, h->Atil4, h->n_pad, h->m_pad, h->n, s));
+  if (h->m_pad > 0 && !h->fold) CIP_TRY(cone_scale_panel(h->cd, h->Fi, h->At4, h->Atil4, h->n_pad, h->m_pad, h->n, s));
   CIP_CUDA(cudaEventRecord(h->ev[1], s));
   const double* cin = (h->rank == 0) ? h->Qq4 : nullptr;
   // rows of Atil beyond m_pad hold sqrt(rho)*G (constant): H' = Q + Atil'Atil + rho G'G, added on rank 0 only
@@ -302,7 +306,9 @@ int form_H(cip_engine* h) {
     a.x_row0 = a.y_row0 = 0; a.x_kq0 = a.y_kq0 = 0; a.nk = k_rows / 32;
     a.Cin = cin; a.Cout = h->H4; a.ldc = h->n_pad; a.c_row0 = a.c_col0 = 0; a.alpha = 1.0;
     a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES;        // tall-skinny A (n << m): split the contraction
-    CIP_TRY(launch_gemm_nt(h->mapAtil, h->mapAtil, a, s));
+    if (h->fold) a.kscale = h->Fi.a;                          // W^-2 applied to the fragments: no Atil4
+    const GemmOperand& op = h->fold ? h->mapAt : h->mapAtil;
+    CIP_TRY(launch_gemm_nt(op, op, a, s));
   } else {
     if (cin) CIP_TRY(vec_copy(h->H4, cin, (size_t)h->n_pad * h->n_pad, s));
     else CIP_TRY(fill_zero(h->H4, (size_t)h->n_pad * h->n_pad, s));
@@ -593,7 +599,22 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
     h->aug_rho = (p > 0) ? rho : 0.0;
     h->aug_rows = (h->aug_rho > 0) ? round_up(p, 32) : 0;
   }
-  CIP_TRY(dev_alloc(h, &h->Atil4, (size_t)(h->m_pad + h->aug_rows) * h->n_pad));
+  {
+    // fold the scaling into the SYRK (no Atil4) for pure R-cone problems: on request, or when the second copy of
+    // A would not fit next to what is still to be allocated (Q, H, workspaces: ~ 3 n_pad^2 + 2.2 GB)
+    const bool can = slist.empty() && qlist.empty() && h->aug_rows == 0 && m > 0;
+    const bool has_field = opts_size(opts) >= offsetof(cip_options, fold_scaling) + sizeof(int);
+    int mode = !can ? 2 : (has_field ? h->opt.fold_scaling : 0);
+    if (const char* env = getenv("CIP_FOLD_SCALING")) { if (can) mode = atoi(env); }
+    if (mode == 0) {
+      size_t free_b = 0, total_b = 0;
+      CIP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t need = mn * 8 + 3 * nn * 8 + (size_t)GEMM_WS_DOUBLES * 8 + (size_t(1) << 30);
+      mode = (free_b < need) ? 1 : 2;
+    }
+    h->fold = (mode == 1);
+  }
+  if (!h->fold) CIP_TRY(dev_alloc(h, &h->Atil4, (size_t)(h->m_pad + h->aug_rows) * h->n_pad));
   CIP_TRY(dev_alloc(h, &h->Qq4, nn));
   CIP_TRY(dev_alloc(h, &h->H4, nn));
   CIP_TRY(dev_alloc(h, &h->gemm_ws, (size_t)GEMM_WS_DOUBLES));
@@ -656,7 +677,8 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
       cudaFree(stg);
     }
   }
-  if (h->m_pad + h->aug_rows > 0)
+  if (h->fold) CIP_TRY(make_q4_tensor_map(&h->mapAt.map, h->At4, h->n_pad, h->m_pad / 4));
+  else if (h->m_pad + h->aug_rows > 0)
     CIP_TRY(make_q4_tensor_map(&h->mapAtil.map, h->Atil4, h->n_pad, (h->m_pad + h->aug_rows) / 4));
   CIP_TRY(chol_make_plan(&h->cholH, h->H4, h->n_pad, h->Winv, h->info));
 

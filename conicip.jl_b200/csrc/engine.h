@@ -39,6 +39,8 @@ struct cip_engine {
   cip::Scaling F{}, Fi{};
   bool have_scaling = false, have_factor = false;
   double* gemm_ws = nullptr;   // split-K workspace of gemm_nt (GEMM_WS_DOUBLES)
+  bool fold = false;           // R-only handle without Atil4: the SYRK reads At4 and scales in registers (opts.fold_scaling)
+  cip::GemmOperand mapAt{};
   int aug_rows = 0;        // rows of Atil4 beyond m_pad holding sqrt(aug_rho) * G
   double aug_rho = 0.0;
   // work vectors

@@ -23,7 +23,7 @@ constexpr int STAGE_DOUBLES = 4 * BOX_DOUBLES;   // 64 KB
 constexpr int CONSUMER_WARPS = 8;
 constexpr int BAND = 12;
 constexpr int NUM_THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128 + STAGES * KT * 8;   // tiles | barriers | k scales per stage
 
 __device__ __forceinline__ void tile_of(const GemmArgs& a, int t, int& ti, int& tj) {
   if (a.lower) {
@@ -55,6 +55,7 @@ __device__ __forceinline__ void tile_of(const GemmArgs& a, int t, int& ti, int& 
   }
 }
 
+template <bool SCALED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const GemmArgs a) {
@@ -62,6 +63,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   double* tiles = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8);
   uint64_t* empty = full + STAGES;
+  double* kscales = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * STAGE_DOUBLES * 8 + 128);   // [STAGES][KT]
 
   int ti, tj;
   // CTAs below tail0 own a whole tile; above it, ksplit consecutive CTAs share one (k tiles [kt0, kt1))
@@ -91,7 +93,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tma_prefetch_desc(&tmY);
       const int xr = (a.x_row0 + ti * BM) * 4;
       const int yr = (a.y_row0 + tj * BN) * 4;
-      const uint32_t bytes = same ? 2u * BOX_BYTES : 4u * BOX_BYTES;
+      const uint32_t bytes = (same ? 2u * BOX_BYTES : 4u * BOX_BYTES) + (SCALED ? (uint32_t)(KT * 8) : 0u);
       for (int kt = kt0; kt < kt1; ++kt) {
         const int s = (kt - kt0) % STAGES;
         const uint32_t ph = (uint32_t)((kt - kt0) / STAGES) & 1u;
@@ -104,6 +106,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tma_load_2d(st + 2 * BOX_DOUBLES, &tmY, &full[s], yr, a.y_kq0 + kt * KQ);
           tma_load_2d(st + 3 * BOX_DOUBLES, &tmY, &full[s], yr + HALF * 4, a.y_kq0 + kt * KQ);
         }
+        if (SCALED)      // the 32 row factors of this k tile (1-D bulk copy onto the same barrier)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(kscales + s * KT)),
+                       "l"(a.kscale + (size_t)(a.y_kq0 + kt * KQ) * 4), "r"((uint32_t)(KT * 8)), "r"(smem_u32(&full[s]))
+                       : "memory");
       }
     }
     return;
@@ -136,6 +143,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int mi = 0; mi < 8; ++mi) av[mi] = xs[(q * HALF + mi * 8) * 4];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) bv[ni] = ys[(q * HALF + ni * 8) * 4];
+      if (SCALED) {                                   // B fragment element (k = 4q + t, n = g): scale by w_k^2
+        const double w = kscales[s * KT + q * 4 + t];
+        const double w2 = w * w;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bv[ni] *= w2;
+      }
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -233,7 +246,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                     CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
-std::atomic<unsigned long long> g_attr_set{0};
+std::atomic<unsigned long long> g_attr_set{0}, g_attr_set_scaled{0};
 }  // namespace
 
 int gemm_nt_smem_bytes() { return SMEM_BYTES; }
@@ -275,7 +288,8 @@ int unpack_tile_major(const GemmArgs& a, cudaStream_t stream) {
 }
 
 int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a, cudaStream_t stream) {
-  CIP_TRY(ensure_dyn_smem((const void*)gemm_nt_kernel, SMEM_BYTES, &g_attr_set));
+  CIP_TRY(ensure_dyn_smem((const void*)gemm_nt_kernel<false>, SMEM_BYTES, &g_attr_set));
+  if (a.kscale) CIP_TRY(ensure_dyn_smem((const void*)gemm_nt_kernel<true>, SMEM_BYTES, &g_attr_set_scaled));
   const int nsm = sm_count();      // one CTA per SM (192 KB of shared memory each): a wave is nsm tiles
   const long long all_tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
   const long long tiles = a.tile_count > 0 ? a.tile_count : all_tiles - a.tile_begin;
@@ -302,7 +316,8 @@ int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a
     }
   }
   const long long ctas = b.tail0 + (tiles - b.tail0) * b.ksplit;
-  gemm_nt_kernel<<<(unsigned)ctas, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, b);
+  if (a.kscale) gemm_nt_kernel<true><<<(unsigned)ctas, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, b);
+  else gemm_nt_kernel<false><<<(unsigned)ctas, NUM_THREADS, SMEM_BYTES, stream>>>(X.map, Y.map, b);
   CIP_CHECK_LAUNCH();
   if (b.ksplit > 1) {
     splitk_reduce_kernel<<<(unsigned)(tiles - b.tail0), 256, 0, stream>>>(b);

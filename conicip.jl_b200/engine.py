@@ -36,7 +36,7 @@ class Engine:
     """LEVEL-1 object: `kktsolver(Q, A, G, cone_dims)` (src/ConicIP.jl:667)."""
 
     def __init__(self, Q, A, G, cone_dims, *, reg_delta=0.0, reg_eps_G=0.0, device=-1,
-                 use_torch_stream=True, dist_chol=-1, aug_rho=-1.0, ngpus=1):
+                 use_torch_stream=True, dist_chol=-1, aug_rho=-1.0, ngpus=1, fold_scaling=0):
         L = lib()
         self.cone_dims = [(t, int(k)) for t, k in cone_dims]
         self.cone_type = np.array([CONE_CODE[t] for t, _ in self.cone_dims], dtype=np.int32)
@@ -53,6 +53,7 @@ class Engine:
         opts.dist_chol = dist_chol
         opts.aug_rho = aug_rho
         opts.ngpus = int(ngpus)            # > 1: single-process multi-GPU handle (global vectors in and out)
+        opts.fold_scaling = int(fold_scaling)   # 0 auto, 1 always, 2 never (R-only problems: no Atil copy of A)
         self.ngpus = max(1, int(ngpus))
         self._torch = None
         self._use_torch_stream = use_torch_stream

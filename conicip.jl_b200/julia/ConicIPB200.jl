@@ -30,7 +30,12 @@ struct Options            # mirrors cip_options
     verbose::Cint
     dist_chol::Cint
     aug_rho::Cdouble
+    ngpus::Cint           # > 1: this one process drives that many GPUs behind the handle (rows of A sliced on cone boundaries)
+    fold_scaling::Cint    # 0 auto, 1 always, 2 never: R-only problems without a second (scaled) copy of A
 end
+make_options(; device = -1, reg_delta = 0.0, q_kind = 0, ngpus = 1, fold_scaling = 0) =
+    Options(Cint(sizeof(Options)), Cint(device), reg_delta, 0.0, Cint(q_kind), Cint(0), Cint(-1), -1.0, Cint(ngpus),
+            Cint(fold_scaling))
 
 lasterr() = unsafe_string(ccall((:cip_last_error, LIB), Cstring, ()))
 function check(rc::Cint)
@@ -51,13 +56,13 @@ Csc(M::SparseMatrixCSC{Float64,Int64}) = Csc(size(M, 1), size(M, 2), pointer(M.c
 mutable struct Engine
     h::Ptr{Cvoid}
     n::Int; m::Int; p::Int
-    function Engine(Q, A, G, cone_dims; reg_delta = 0.0)
+    function Engine(Q, A, G, cone_dims; reg_delta = 0.0, ngpus = 1, device = -1, fold_scaling = 0)
         n = size(Q, 1); m = size(A, 1); p = size(G, 1)
         if A isa SparseMatrixCSC          # sparse LEVEL 1: no dense copy on the host (cip_create_csc)
             Qs = SparseMatrixCSC{Float64,Int64}(sparse(Q)); As = SparseMatrixCSC{Float64,Int64}(A)
             Gs = SparseMatrixCSC{Float64,Int64}(sparse(G))
             ct = Cint[CONE_CODE[t] for (t, _) in cone_dims]; cdim = Cint[k for (_, k) in cone_dims]
-            opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, Cint(2), Cint(0), Cint(-1), -1.0))
+            opts = Ref(make_options(; device, reg_delta, q_kind = 2, ngpus, fold_scaling))
             hp = Ref{Ptr{Cvoid}}(C_NULL)
             GC.@preserve Qs As Gs begin
                 rc = ccall((:cip_create_csc, LIB), Cint,
@@ -76,7 +81,7 @@ mutable struct Engine
         Gd = Matrix{Float64}(G)
         ct = Cint[CONE_CODE[t] for (t, _) in cone_dims]
         cdim = Cint[k for (_, k) in cone_dims]
-        opts = Ref(Options(Cint(sizeof(Options)), Cint(-1), reg_delta, 0.0, qk, Cint(0), Cint(-1), -1.0))
+        opts = Ref(make_options(; device, reg_delta, q_kind = qk, ngpus, fold_scaling))
         hp = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:cip_create, LIB), Cint,
                    (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint,
@@ -101,6 +106,10 @@ function flatten(F::Block)
         if B isa Diagonal
             kind[i] = BLK_DIAG; append!(fa, B.diag); append!(fb, zeros(length(B.diag)))
         elseif B isa SymWoodbury
+            # only the rank-1 form nestod_soc builds (src/ConicIP.jl:192) has a flat representation; the general
+            # WoodburyMatrices form (matrix B, matrix D: src/blockmatrices.jl:135-141) is rejected, not mangled
+            (size(B.B, 2) == 1 && length(B.D) == 1) ||
+                error("ConicIPB200: SymWoodbury blocks of rank > 1 are not supported (block $i has rank $(size(B.B, 2)))")
             kind[i] = BLK_WOODBURY
             append!(fa, B.A.diag); append!(fb, vec(B.B)); fD[i] = B.D isa Number ? B.D : B.D[1, 1]
         elseif B isa VecCongurance
@@ -119,8 +128,8 @@ end
 Drop-in for `kktsolver_qr` / `pivot(kktsolver_2x2)`; three-level closure protocol of
 docs/src/guides/kkt_solvers.md:84-109.
 """
-function kktsolver_b200(Q, A, G, cone_dims)
-    eng = Engine(Q, A, G, cone_dims)                                  # LEVEL 1: upload once
+function kktsolver_b200(Q, A, G, cone_dims; engine_options...)
+    eng = Engine(Q, A, G, cone_dims; engine_options...)               # LEVEL 1: upload once
 
     function solve3x3gen(F, F⁻ᵀ)                                      # LEVEL 2: form H, factor
         kind, fa, fb, fD, fR = flatten(F)
@@ -147,6 +156,13 @@ function kktsolver_b200(Q, A, G, cone_dims)
     end
     return solve3x3gen
 end
+"""
+    kktsolver_b200(; ngpus = 8, ...) -> kktsolver
+
+Options bound: `conicIP(Q, c, A, b, cone_dims, G, d; kktsolver = kktsolver_b200(ngpus = 8))` row-shards `A` over
+eight GPUs of this process behind the one callback the reference makes (src/ConicIP.jl:667).
+"""
+kktsolver_b200(; engine_options...) = (Q, A, G, cone_dims) -> kktsolver_b200(Q, A, G, cone_dims; engine_options...)
 
 # ---- cone kernels (no callback exists for these in conicIP; a device-resident driver calls them)
 nt_scaling!(eng::Engine, v, s, λ) = check(ccall((:cip_nt_scaling, LIB), Cint,
@@ -180,8 +196,8 @@ const STATUS = (:None, :Optimal, :Infeasible, :Unbounded, :Abandoned, :Error)
 function conicIP_b200(Q, c::AbstractVector, A, b::AbstractVector, cone_dims,
                       G = spzeros(0, length(c)), d = zeros(0);
                       optTol = 1e-6, DTB = 0.01, verbose = false, maxRefinementSteps = 3, maxIters = 100,
-                      infeasTol = optTol, refinementThreshold = optTol / 1e7)
-    eng = Engine(Q, A, G, cone_dims)
+                      infeasTol = optTol, refinementThreshold = optTol / 1e7, ngpus = 1, device = -1)
+    eng = Engine(Q, A, G, cone_dims; ngpus, device)
     y = Vector{Float64}(undef, eng.n); w = Vector{Float64}(undef, eng.p); v = Vector{Float64}(undef, eng.m)
     opts = Ref(IpmOptions(Cint(sizeof(IpmOptions)), maxIters, maxRefinementSteps, verbose, optTol, DTB, infeasTol,
                           refinementThreshold))
@@ -207,13 +223,76 @@ function imcols_b200(A, b, ϵ = 1e-8; device = -1)
 end
 # `preprocess_conicIP` itself needs no change beyond calling imcols_b200 at src/preprocessor.jl:58-59.
 
-# ---- MOI: `ConicIP.Optimizer` has no kktsolver field (src/MOI_wrapper.jl:19-31) and optimize!
-# forwards only verbose/optTol/maxIters (:278-282).  The one-field extension a maintainer adds:
+# ---- MOI / JuMP (SURVEY 8f rank 2).  `ConicIP.Optimizer` has no kktsolver field (src/MOI_wrapper.jl:19-31) and
+# `optimize!` forwards only verbose / optTol / maxIters to `preprocess_conicIP` (:278-282), which itself forwards any
+# extra option to `conicIP` (src/preprocessor.jl:44,82-84).  Two ways to select the engine from JuMP:
 #
-#     mutable struct Optimizer ...; kktsolver::Function; end          # default ConicIP.kktsolver_qr
-#     sol = preprocess_conicIP(Q, c, A, b, cone_dims, G, d; verbose, optTol, maxIters,
-#                              kktsolver = optimizer.kktsolver)       # preprocessor forwards options... (:44,:82-84)
+#  (1) the two-line patch `julia/MOI_wrapper_kktsolver.patch` (one struct field, one keyword), after which
+#          model = Model(() -> ConicIP.Optimizer(kktsolver = ConicIPB200.kktsolver_b200(ngpus = 8)))
 #
-# after which `ConicIP.Optimizer(kktsolver = ConicIPB200.kktsolver_b200)` selects the engine.
+#  (2) without touching ConicIP.jl: `ConicIPB200.Optimizer`, a wrapper optimizer that owns a stock
+#      `ConicIP.Optimizer`, delegates the whole MOI interface to it, and for the solve itself re-runs the stock
+#      `optimize!` with `ConicIP.preprocess_conicIP` intercepted so that `kktsolver =` is added to its options.
+import MathOptInterface
+const MOI = MathOptInterface
+
+"""
+    ConicIPB200.Optimizer(; ngpus = 1, verbose = false, optTol = 1e-6, maxIters = 100)
+
+Drop-in for `ConicIP.Optimizer` (src/MOI_wrapper.jl:19-40) whose KKT systems are solved by the B200 engine.
+"""
+mutable struct Optimizer <: MOI.AbstractOptimizer
+    inner::ConicIP.Optimizer
+    kktsolver::Function
+end
+Optimizer(; ngpus = 1, device = -1, kwargs...) = Optimizer(ConicIP.Optimizer(; kwargs...), kktsolver_b200(; ngpus, device))
+
+# the model data path of the stock optimizer is re-used as it is (constraint extraction :102-136, :185-275)
+for f in (:empty!, :is_empty)
+    @eval MOI.$f(o::Optimizer) = MOI.$f(o.inner)
+end
+MOI.get(::Optimizer, ::MOI.SolverName) = "ConicIP (B200 KKT engine)"
+MOI.get(o::Optimizer, attr::MOI.AnyAttribute, args...) = MOI.get(o.inner, attr, args...)
+MOI.supports(o::Optimizer, attr::MOI.AnyAttribute, args...) = MOI.supports(o.inner, attr, args...)
+MOI.supports_constraint(o::Optimizer, F::Type{<:MOI.AbstractFunction}, S::Type{<:MOI.AbstractSet}) =
+    MOI.supports_constraint(o.inner, F, S)
+MOI.set(o::Optimizer, attr::MOI.AnyAttribute, args...) = MOI.set(o.inner, attr, args...)
+
+# `optimize!(dest, src)` (src/MOI_wrapper.jl:142-285) builds Q, c, A, b, cone_dims, G, d and calls
+# `preprocess_conicIP(...; verbose, optTol, maxIters)` at :278.  The solve is re-issued through the same function
+# with the engine's kktsolver appended to the options, by shadowing the name in a module that `include`s the
+# stock wrapper code path unchanged:
+function MOI.optimize!(dest::Optimizer, src::MOI.ModelLike)
+    return with_kktsolver(dest.kktsolver) do
+        MOI.optimize!(dest.inner, src)
+    end
+end
+# task-local override consulted by the patched-in keyword default below
+const KKTSOLVER_OVERRIDE = Ref{Union{Nothing,Function}}(nothing)
+function with_kktsolver(f, k::Function)
+    old = KKTSOLVER_OVERRIDE[]
+    KKTSOLVER_OVERRIDE[] = k
+    try
+        return f()
+    finally
+        KKTSOLVER_OVERRIDE[] = old
+    end
+end
+# `conicIP`'s keyword default is `kktsolver = kktsolver_qr` (src/ConicIP.jl:498); the reference exports that
+# function, so a method on it that consults the override routes every stock call site -- including the one
+# `optimize!` reaches through `preprocess_conicIP` -- to the engine while a `ConicIPB200.Optimizer` is solving,
+# and falls back to the stock QR solver otherwise.
+const _stock_qr = ConicIP.kktsolver_qr
+function routed_kktsolver(Q, A, G, cone_dims)
+    k = KKTSOLVER_OVERRIDE[]
+    return k === nothing ? _stock_qr(Q, A, G, cone_dims) : k(Q, A, G, cone_dims)
+end
+# Installing the route is one assignment in ConicIP's namespace (done once, at `using ConicIPB200`); with the
+# patch of (1) applied it is unnecessary and skipped.
+function __init__()
+    if !(:kktsolver in fieldnames(ConicIP.Optimizer))
+        @eval ConicIP kktsolver_qr(Q, A, G, cone_dims) = $(routed_kktsolver)(Q, A, G, cone_dims)
+    end
+end
 
 end # module

@@ -66,6 +66,10 @@ typedef struct cip_options {
                            calling thread's single call -- the reference calls its kktsolver once from one process
                            (src/ConicIP.jl:667), so this is what `kktsolver = kktsolver_b200(ngpus = 8)` uses.
                            Every entry point below then takes and returns GLOBAL vectors; 0 / 1 = one device */
+  int    fold_scaling;  /* K = R^m only (every block of F diagonal): apply W^-2 to the operand fragments inside the
+                           SYRK instead of materialising Atil = F^-T A (src/kktsolvers.jl:33) -- halves the resident
+                           bytes (no second copy of A), costs ~1.5 % of the SYRK.  0: auto (fold when the second copy
+                           would not fit in free device memory), 1: always, 2: never */
 } cip_options;
 
 typedef struct cip_stats_t {
@@ -74,7 +78,7 @@ typedef struct cip_stats_t {
   double ms_scale, ms_syrk, ms_allreduce, ms_chol, ms_schur, ms_solve; /* last call, CUDA events */
   double syrk_flops;                    /* algorithmic m*n^2 of the last SYRK (local rows) */
   double chol_flops;                    /* n^3/3                                           */
-  size_t device_bytes;                  /* bytes held by this handle                       */
+  size_t device_bytes;                  /* bytes held by this handle (all devices of a multi-GPU handle) */
   long long kernel_launches;            /* kernels launched by this library so far         */
 } cip_stats_t;
 

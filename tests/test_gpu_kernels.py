@@ -301,3 +301,36 @@ def test_regularisation_option():
     assert eng.factor(cb.Block([cb.Diagonal(np.ones(2))])) == 0
     assert np.allclose(np.diag(eng.get_H()), 0.5)                            # chol(0.25 I)
     eng.close()
+
+
+def test_folded_scaling_matches_materialised_panel():
+    """opts.fold_scaling: for K = R^m the SYRK applies W^-2 to its operand fragments and the handle keeps no
+    Atil = F^-T A (src/kktsolvers.jl:33).  Same H (up to the order in which the two factors of w^2 meet the
+    products), same solve, about half the resident bytes."""
+    import conicip_b200 as cb
+    rng = np.random.default_rng(77)
+    for n, m in [(300, 2000), (128, 4096), (1000, 1000)]:
+        A = rng.standard_normal((m, n)) / np.sqrt(n)
+        Q = np.diag(rng.uniform(1, 2, n))
+        v, s = rng.uniform(1e-3, 1e3, m), rng.uniform(1e-3, 1e3, m)
+        ry, rv = rng.standard_normal(n), rng.standard_normal(m)
+        e0 = cb.Engine(Q, A, None, [("R", m)], fold_scaling=2)
+        e1 = cb.Engine(Q, A, None, [("R", m)], fold_scaling=1)
+        assert e1.stats()["device_bytes"] < e0.stats()["device_bytes"] - 8 * m * n // 2
+        for e in (e0, e1):
+            e.nt_scaling(v, s)
+            e.form_H()
+        H0, H1 = np.tril(e0.get_H()), np.tril(e1.get_H())
+        assert np.linalg.norm(H1 - H0) <= 1e-13 * np.linalg.norm(H0)
+        want = Q + (A.T * (v / s)) @ A
+        assert np.linalg.norm(H1 - np.tril(want)) <= 1e-12 * np.linalg.norm(want)
+        assert e0.factor_H() == 0 and e1.factor_H() == 0
+        (dy0, _, dv0), (dy1, _, dv1) = e0.solve(ry, None, rv), e1.solve(ry, None, rv)
+        assert np.linalg.norm(dy1 - dy0) <= 1e-9 * np.linalg.norm(dy0)
+        assert np.linalg.norm(dv1 - dv0) <= 1e-9 * np.linalg.norm(dv0)
+        # the host Block path (cip_factor with DIAG kinds) folds as well
+        F = cb.Block([cb.Diagonal(np.sqrt(s / v))])
+        assert e1.factor(F) == 0
+        dy2, _, dv2 = e1.solve(ry, None, rv)
+        assert np.linalg.norm(dy2 - dy0) <= 1e-9 * np.linalg.norm(dy0)
+        e0.close(); e1.close()

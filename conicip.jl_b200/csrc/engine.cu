@@ -574,6 +574,13 @@ int create_body(cip_engine* h, int n, int m, int p, const double* Q, int ldq, co
   h->cd.row_cone = h->d_rowcone; h->cd.qlist = h->d_qlist; h->cd.nq = (int)qlist.size();
   h->cd.slist = h->d_slist; h->cd.ns = (int)slist.size(); h->cd.max_q_dim = maxq; h->cd.max_s_ord = maxs;
   h->cd.sord = h->d_sord; h->cd.roff = h->d_roff;
+  h->cd.sws = nullptr; h->cd.sws_stride = sdp_workspace_doubles(maxs);
+  if (h->cd.sws_stride > 0) {
+    // one slice per CTA of the widest S-cone launch (the scaled panel: ns x chunks)
+    const long long ctas = (long long)slist.size() * std::max(1, sdp_panel_chunks(maxs, n));
+    CIP_TRY(dev_alloc(h, &h->d_sws, (size_t)(ctas * h->cd.sws_stride)));
+    h->cd.sws = h->d_sws;
+  }
   h->cd.nr_rows = 0;
   for (int i = 0; i < ncones; ++i)
     if (cone_type[i] == CIP_CONE_R) h->cd.nr_rows += h->h_off[i + 1] - h->h_off[i];
@@ -806,6 +813,7 @@ int cip_destroy(cip_handle h) {
   chol_free_plan(&h->cholH);
   chol_free_plan(&h->cholS);
   if (h->Hp) cudaFree(h->Hp);
+  if (h->d_sws) cudaFree(h->d_sws);
   if (h->cs) cudaStreamDestroy(h->cs);
   if (h->s2) cudaStreamDestroy(h->s2);
   for (auto e : h->evc) if (e) cudaEventDestroy(e);

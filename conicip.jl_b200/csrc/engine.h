@@ -33,6 +33,7 @@ struct cip_engine {
   std::vector<int> h_type, h_off;
   int *d_type = nullptr, *d_off = nullptr, *d_rowcone = nullptr, *d_qlist = nullptr, *d_slist = nullptr;
   int *d_sord = nullptr, *d_roff = nullptr;
+  double* d_sws = nullptr;     // S-cone workspace (orders above 64)
   std::vector<int> h_slist, h_sord, h_roff;
   size_t r_total = 0;
   cip::ConeDesc cd{};

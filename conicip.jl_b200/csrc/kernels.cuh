@@ -51,6 +51,8 @@ struct ConeDesc {
   int max_s_ord;
   const int* sord;      // [ns] matrix order k of every S cone (slist order)
   const int* roff;      // [ns] offset (in doubles) of its k*k block inside Scaling::R / Ri
+  double* sws;          // global workspace of the S-cone kernels for orders above 64 (nullptr if none)
+  long long sws_stride; // doubles per CTA
 };
 struct Scaling {   // flattened block-diagonal operator: per cone  diag(a) + D * b b'   (kind 1) or diag(a) (kind 0)
   int* kind;       // [ncones]
@@ -81,6 +83,8 @@ int cone_scale_panel(const ConeDesc& c, Scaling Fi, const double* At4, double* A
 
 // ---------------------------------------------------------------- S (PSD) cones (sdp.cu)
 int sdp_max_order();
+long long sdp_workspace_doubles(int k);          // per CTA, 0 when the order fits shared memory
+int sdp_panel_chunks(int max_order, int ncols);  // grid.y of the S rows of the scaled panel
 int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, const double* x, double* y,
               cudaStream_t st);
 int sdp_nt_scaling(const ConeDesc& c, Scaling F, Scaling Fi, const double* v, const double* s, double* lambda,

@@ -6,6 +6,8 @@
 // (Hestenes) Jacobi iteration, which has high relative accuracy for the SVD the NT scaling needs.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "../../include/conicip_b200.h"
 
@@ -13,19 +15,20 @@ namespace cip {
 
 namespace {
 
-constexpr int KMAX = 64;
-constexpr int LDM = KMAX + 1;          // padded leading dimension of every shared k x k matrix
+constexpr int KMAX = 64;               // up to this order the four k x k work matrices of a cone live in shared memory
+constexpr int KCAP = 512;              // larger orders run the same code on a per-CTA workspace in global memory (L2)
+constexpr int LDM = KMAX + 1;          // padded leading dimension of the shared k x k matrices
 constexpr int MAT = KMAX * LDM;        // doubles per shared matrix
 constexpr int NT = 256;                // threads per CTA
 #define SQRT2 1.4142135623730951
-#define M(A, i, j) (A)[(j) * LDM + (i)]   // column-major
+#define M(A, i, j) (A)[(j) * ldm + (i)]   // column-major; `ldm` (LDM in shared memory, k + 1 in the workspace) is in scope everywhere
 
 __device__ __forceinline__ int svec_index(int i, int j, int k) {   // i <= j, row-major upper triangle
   return i * k - (i * (i - 1)) / 2 + (j - i);
 }
 
 // X = mat(x)   (src/ConicIP.jl:93-119)
-__device__ void load_mat(double* X, const double* __restrict__ x, int k) {
+__device__ void load_mat(double* X, const double* __restrict__ x, int k, int ldm) {
   for (int e = threadIdx.x; e < k * k; e += NT) {
     const int i = e % k, j = e / k;
     const int a = i < j ? i : j, b = i < j ? j : i;
@@ -34,7 +37,7 @@ __device__ void load_mat(double* X, const double* __restrict__ x, int k) {
   }
 }
 // y = vecm(Y)  (src/ConicIP.jl:128-151); Y is symmetrised as (Y + Y')/2 to wash out rounding asymmetry
-__device__ void store_vecm(double* __restrict__ y, const double* Y, int k, bool accumulate = false) {
+__device__ void store_vecm(double* __restrict__ y, const double* Y, int k, int ldm, bool accumulate = false) {
   for (int e = threadIdx.x; e < k * k; e += NT) {
     const int i = e % k, j = e / k;
     if (i <= j) {
@@ -47,7 +50,7 @@ __device__ void store_vecm(double* __restrict__ y, const double* Y, int k, bool 
 }
 // C = op(A) * op(B), k x k, all in shared memory (C must not alias A or B)
 template <bool TA, bool TB>
-__device__ void matmul(double* C, const double* A, const double* B, int k) {
+__device__ void matmul(double* C, const double* A, const double* B, int k, int ldm) {
   for (int e = threadIdx.x; e < k * k; e += NT) {
     const int i = e % k, j = e / k;
     double s = 0.0;
@@ -57,7 +60,7 @@ __device__ void matmul(double* C, const double* A, const double* B, int k) {
 }
 // In-place lower Cholesky of a symmetric matrix; strict upper triangle zeroed.  Returns false in
 // *ok (shared) when a pivot is not positive.
-__device__ void cholesky(double* A, int k, int* ok) {
+__device__ void cholesky(double* A, int k, int* ok, int ldm) {
   if (threadIdx.x == 0) *ok = 1;
   __syncthreads();
   for (int c = 0; c < k; ++c) {
@@ -84,7 +87,7 @@ __device__ void cholesky(double* A, int k, int* ok) {
   __syncthreads();
 }
 // X = inv(L) for lower-triangular L (X lower-triangular, distinct buffer)
-__device__ void tri_inverse(double* X, const double* L, int k) {
+__device__ void tri_inverse(double* X, const double* L, int k, int ldm) {
   for (int e = threadIdx.x; e < k * k; e += NT) M(X, e % k, e / k) = 0.0;
   __syncthreads();
   // column j of X solves L x = e_j; one thread per column (k <= 64 columns, forward substitution)
@@ -100,7 +103,7 @@ __device__ void tri_inverse(double* X, const double* L, int k) {
 // One-sided (Hestenes) Jacobi: rotates the columns of G (and of V, if non-null, starting from
 // whatever V holds) until they are mutually orthogonal: G_out = G_in * J, V_out = V_in * J.
 // Round-robin ordering; each of the k/2 disjoint pairs of a step is handled by 8 lanes.
-__device__ void jacobi_onesided(double* G, double* V, int k, int* sh_flag) {
+__device__ void jacobi_onesided(double* G, double* V, int k, int* sh_flag, int ldm) {
   const int kk = (k + 1) & ~1;                 // even number of players (a phantom column if k is odd)
   const int pairs = kk / 2;
   const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 32 groups of 8 lanes
@@ -155,14 +158,26 @@ __device__ void jacobi_onesided(double* G, double* V, int k, int* sh_flag) {
 
 struct SMem {
   double* A; double* B; double* C; double* D;   // four k x k matrices
-  double* vec;                                  // KMAX doubles
+  double* vec;                                  // k doubles
   int* flag;
+  int ldm;
 };
-__device__ __forceinline__ SMem carve(double* base) {
+// k <= KMAX: everything in dynamic shared memory; above: this CTA's slice of the global workspace (the flag stays
+// in shared memory).  `cta` = linear CTA index of the launch.
+__device__ __forceinline__ SMem carve(double* base, int k, double* ws, long long ws_stride, int cta) {
   SMem s;
-  s.A = base; s.B = base + MAT; s.C = base + 2 * MAT; s.D = base + 3 * MAT;
-  s.vec = base + 4 * MAT;
-  s.flag = reinterpret_cast<int*>(s.vec + KMAX);
+  s.flag = reinterpret_cast<int*>(base + 4 * MAT + KMAX);
+  if (k <= KMAX) {
+    s.ldm = LDM;
+    s.A = base; s.B = base + MAT; s.C = base + 2 * MAT; s.D = base + 3 * MAT;
+    s.vec = base + 4 * MAT;
+  } else {
+    s.ldm = k + 1;
+    double* g = ws + (size_t)cta * (size_t)ws_stride;
+    const size_t mat = (size_t)k * (k + 1);
+    s.A = g; s.B = g + mat; s.C = g + 2 * mat; s.D = g + 3 * mat;
+    s.vec = g + 4 * mat;
+  }
   return s;
 }
 constexpr int SDP_SMEM = (4 * MAT + KMAX) * 8 + 16;
@@ -171,6 +186,7 @@ constexpr int SDP_SMEM = (4 * MAT + KMAX) * 8 + 16;
 // eigenvectors -> s.B (if want_vectors).  Uses the shift M + c I (c = ||M||_F) so that the one-sided
 // Jacobi sees a PSD matrix and singular values equal eigenvalues.
 __device__ void sym_eigen(SMem s, int k, bool want_vectors) {
+  const int ldm = s.ldm;
   double* A = s.A; double* V = s.B;
   double fro = 0.0;
   for (int e = threadIdx.x; e < k * k; e += NT) { const double v = M(A, e % k, e / k); fro = fma(v, v, fro); }
@@ -187,7 +203,7 @@ __device__ void sym_eigen(SMem s, int k, bool want_vectors) {
     M(V, i, j) = (i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
-  jacobi_onesided(A, V, k, s.flag);
+  jacobi_onesided(A, V, k, s.flag, ldm);
   // columns of A are now (lambda_j + c) v_j: lambda_j = v_j . a_j - c
   for (int j = threadIdx.x; j < k; j += NT) {
     double d = 0.0;
@@ -204,6 +220,8 @@ struct SDesc {
   const int* off;     // cone row offsets
   const int* sord;    // order k per S cone (slist order)
   const int* roff;    // offset (doubles) into R / Ri per S cone
+  double* ws;         // global workspace for orders above KMAX (nullptr if none), ws_stride doubles per CTA
+  long long ws_stride;
 };
 
 // y_I = vecm(A' mat(x_I) A) with A = R, R', inv(R), inv(R)' selected by (use_inv, transpose)
@@ -211,25 +229,26 @@ __global__ void __launch_bounds__(NT)
 sdp_apply_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ R, const double* __restrict__ Ri,
                  int use_inv, int transpose, const double* __restrict__ x, double* __restrict__ y) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   if (kind[ci] != CIP_BLK_VECCONG) return;
   const int k = d.sord[si], off = d.off[ci];
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
   const double* src = (use_inv ? Ri : R) + d.roff[si];
   for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) = src[e];
-  load_mat(s.B, x + off, k);
+  load_mat(s.B, x + off, k, ldm);
   __syncthreads();
   if (!transpose) {
-    matmul<false, false>(s.C, s.B, s.A, k);     // X A
+    matmul<false, false>(s.C, s.B, s.A, k, ldm);     // X A
     __syncthreads();
-    matmul<true, false>(s.D, s.A, s.C, k);      // A' (X A)
+    matmul<true, false>(s.D, s.A, s.C, k, ldm);      // A' (X A)
   } else {
-    matmul<false, true>(s.C, s.B, s.A, k);      // X A'
+    matmul<false, true>(s.C, s.B, s.A, k, ldm);      // X A'
     __syncthreads();
-    matmul<false, false>(s.D, s.A, s.C, k);     // A (X A')
+    matmul<false, false>(s.D, s.A, s.C, k, ldm);     // A (X A')
   }
   __syncthreads();
-  store_vecm(y + off, s.D, k);
+  store_vecm(y + off, s.D, k, ldm);
 }
 
 // nestod_sdc (src/ConicIP.jl:196-210): R = inv(Lz)' U sqrt(Lambda), U Lambda V' = svd(Lz' Ls);
@@ -239,16 +258,17 @@ sdp_nt_kernel(SDesc d, int* __restrict__ kindF, int* __restrict__ kindFi, double
               double* __restrict__ Ri, const double* __restrict__ v, const double* __restrict__ sv,
               double* __restrict__ lambda, int* __restrict__ info) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   const int k = d.sord[si], off = d.off[ci];
-  load_mat(s.A, sv + off, k);      // S
-  load_mat(s.B, v + off, k);       // Z
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
+  load_mat(s.A, sv + off, k, ldm);      // S
+  load_mat(s.B, v + off, k, ldm);       // Z
   __syncthreads();
-  cholesky(s.A, k, s.flag);        // Ls
+  cholesky(s.A, k, s.flag, ldm);        // Ls
   const int ok1 = *s.flag;
   __syncthreads();
-  cholesky(s.B, k, s.flag);        // Lz
+  cholesky(s.B, k, s.flag, ldm);        // Lz
   const int ok2 = *s.flag;
   __syncthreads();
   if (!(ok1 && ok2)) {
@@ -260,36 +280,36 @@ sdp_nt_kernel(SDesc d, int* __restrict__ kindF, int* __restrict__ kindFi, double
     for (int e = threadIdx.x; e < dim; e += NT) lambda[off + e] = CUDART_NAN;
     return;
   }
-  matmul<true, false>(s.C, s.B, s.A, k);   // G = Lz' Ls
+  matmul<true, false>(s.C, s.B, s.A, k, ldm);   // G = Lz' Ls
   __syncthreads();
-  jacobi_onesided(s.C, nullptr, k, s.flag);   // C = U Sigma (columns orthogonal)
+  jacobi_onesided(s.C, nullptr, k, s.flag, ldm);   // C = U Sigma (columns orthogonal)
   for (int j = threadIdx.x; j < k; j += NT) {
     double n2 = 0.0;
     for (int i = 0; i < k; ++i) n2 = fma(M(s.C, i, j), M(s.C, i, j), n2);
     s.vec[j] = sqrt(n2);                    // sigma_j
   }
   __syncthreads();
-  tri_inverse(s.D, s.B, k);                 // D = inv(Lz)
+  tri_inverse(s.D, s.B, k, ldm);                 // D = inv(Lz)
   // R = inv(Lz)' * (C * Sigma^-1/2)   ;   inv(R) = Sigma^-3/2 C' Lz'
   for (int e = threadIdx.x; e < k * k; e += NT) { const int j = e / k; M(s.C, e % k, j) /= sqrt(s.vec[j]); }
   __syncthreads();
-  matmul<true, false>(s.A, s.D, s.C, k);    // A = R
+  matmul<true, false>(s.A, s.D, s.C, k, ldm);    // A = R
   __syncthreads();
   double* Rg = R + d.roff[si];
   double* Rig = Ri + d.roff[si];
   for (int e = threadIdx.x; e < k * k; e += NT) Rg[e] = M(s.A, e % k, e / k);
   // inv(R) = (C Sigma^-1/2)' Lz' / sigma  (C already scaled once by Sigma^-1/2)
-  matmul<true, true>(s.D, s.C, s.B, k);     // D = C' Lz'
+  matmul<true, true>(s.D, s.C, s.B, k, ldm);     // D = C' Lz'
   __syncthreads();
   for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k; Rig[e] = M(s.D, i, e / k) / s.vec[i]; }
   // lambda = vecm(R' Z R)
-  load_mat(s.B, v + off, k);
+  load_mat(s.B, v + off, k, ldm);
   __syncthreads();
-  matmul<false, false>(s.C, s.B, s.A, k);
+  matmul<false, false>(s.C, s.B, s.A, k, ldm);
   __syncthreads();
-  matmul<true, false>(s.D, s.A, s.C, k);
+  matmul<true, false>(s.D, s.A, s.C, k, ldm);
   __syncthreads();
-  store_vecm(lambda + off, s.D, k);
+  store_vecm(lambda + off, s.D, k, ldm);
   if (threadIdx.x == 0) { kindF[ci] = CIP_BLK_VECCONG; kindFi[ci] = CIP_BLK_VECCONG; }
 }
 
@@ -297,10 +317,11 @@ sdp_nt_kernel(SDesc d, int* __restrict__ kindF, int* __restrict__ kindFi, double
 __global__ void __launch_bounds__(NT)
 sdp_invert_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ R, double* __restrict__ Ri) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   if (kind[ci] != CIP_BLK_VECCONG) return;
   const int k = d.sord[si];
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
   const double* Rg = R + d.roff[si];
   for (int e = threadIdx.x; e < k * k; e += NT) {
     const int i = e % k, j = e / k;
@@ -344,37 +365,38 @@ __global__ void __launch_bounds__(NT)
 sdp_prod_div_kernel(SDesc d, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ o,
                     int divide) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   const int k = d.sord[si], off = d.off[ci];
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
   if (!divide) {
-    load_mat(s.A, x + off, k);
-    load_mat(s.B, y + off, k);
+    load_mat(s.A, x + off, k, ldm);
+    load_mat(s.B, y + off, k, ldm);
     __syncthreads();
-    matmul<false, false>(s.C, s.A, s.B, k);
+    matmul<false, false>(s.C, s.A, s.B, k, ldm);
     __syncthreads();
     for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k, j = e / k; M(s.D, i, j) = M(s.C, i, j) + M(s.C, j, i); }
     __syncthreads();
-    store_vecm(o + off, s.D, k);
+    store_vecm(o + off, s.D, k, ldm);
     return;
   }
   // Y = V diag(l) V';  T = V' X V;  T_ij /= (l_i + l_j);  O = V T V'
-  load_mat(s.A, y + off, k);
+  load_mat(s.A, y + off, k, ldm);
   __syncthreads();
   sym_eigen(s, k, true);                       // eigenvalues s.vec, vectors s.B
-  load_mat(s.A, x + off, k);
+  load_mat(s.A, x + off, k, ldm);
   __syncthreads();
-  matmul<false, false>(s.C, s.A, s.B, k);      // X V
+  matmul<false, false>(s.C, s.A, s.B, k, ldm);      // X V
   __syncthreads();
-  matmul<true, false>(s.D, s.B, s.C, k);       // V' X V
+  matmul<true, false>(s.D, s.B, s.C, k, ldm);       // V' X V
   __syncthreads();
   for (int e = threadIdx.x; e < k * k; e += NT) { const int i = e % k, j = e / k; M(s.D, i, j) /= (s.vec[i] + s.vec[j]); }
   __syncthreads();
-  matmul<false, true>(s.C, s.D, s.B, k);       // T V'
+  matmul<false, true>(s.C, s.D, s.B, k, ldm);       // T V'
   __syncthreads();
-  matmul<false, false>(s.A, s.B, s.C, k);      // V T V'
+  matmul<false, false>(s.A, s.B, s.C, k, ldm);      // V T V'
   __syncthreads();
-  store_vecm(o + off, s.A, k);
+  store_vecm(o + off, s.A, k, ldm);
 }
 
 __device__ __forceinline__ unsigned long long dkey2(double x) {
@@ -387,34 +409,35 @@ __global__ void __launch_bounds__(NT)
 sdp_maxstep_kernel(SDesc d, const double* __restrict__ x, const double* __restrict__ dd, double d_scale,
                    unsigned long long* key) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   const int k = d.sord[si], off = d.off[ci];
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
   double res;
   if (!dd) {                                       // minimum eigenvalue of X
-    load_mat(s.A, x + off, k);
+    load_mat(s.A, x + off, k, ldm);
     __syncthreads();
     sym_eigen(s, k, false);
     double mn = CUDART_INF;
     for (int j = 0; j < k; ++j) mn = fmin(mn, s.vec[j]);
     res = mn > 0 ? 0.0 : -1.0 + mn;
   } else {
-    load_mat(s.C, x + off, k);
+    load_mat(s.C, x + off, k, ldm);
     __syncthreads();
-    cholesky(s.C, k, s.flag);                      // X = L L'
+    cholesky(s.C, k, s.flag, ldm);                      // X = L L'
     const int ok = *s.flag;
     __syncthreads();
     if (!ok) {
       res = CUDART_INF;                            // X not positive definite (:277-280)
     } else {
-      tri_inverse(s.D, s.C, k);                    // inv(L)
-      load_mat(s.A, dd + off, k);
+      tri_inverse(s.D, s.C, k, ldm);                    // inv(L)
+      load_mat(s.A, dd + off, k, ldm);
       __syncthreads();
       for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) /= d_scale;
       __syncthreads();
-      matmul<false, true>(s.B, s.A, s.D, k);       // D inv(L)'
+      matmul<false, true>(s.B, s.A, s.D, k, ldm);       // D inv(L)'
       __syncthreads();
-      matmul<false, false>(s.A, s.D, s.B, k);      // inv(L) D inv(L)'  (similar to X^-1/2 D X^-1/2)
+      matmul<false, false>(s.A, s.D, s.B, k, ldm);      // inv(L) D inv(L)'  (similar to X^-1/2 D X^-1/2)
       __syncthreads();
       for (int e = threadIdx.x; e < k * k; e += NT) {   // symmetrise, :284
         const int i = e % k, j = e / k;
@@ -437,10 +460,11 @@ sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __re
                        const double* __restrict__ At4, double* __restrict__ Atil4, int ld, int ncols,
                        int cols_per_cta) {
   extern __shared__ double smem[];
-  SMem s = carve(smem);
   const int si = blockIdx.x, ci = d.slist[si];
   if (kind[ci] != CIP_BLK_VECCONG) return;
   const int k = d.sord[si], off = d.off[ci];
+  SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
+  const int ldm = s.ldm;
   const int dim = k * (k + 1) / 2;
   const double* src = Ri + d.roff[si];
   for (int e = threadIdx.x; e < k * k; e += NT) M(s.A, e % k, e / k) = src[e];
@@ -455,9 +479,9 @@ sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __re
       M(s.B, i, c) = (i == c) ? v : v / SQRT2;
     }
     __syncthreads();
-    matmul<false, true>(s.C, s.B, s.A, k);      // X inv(R)'
+    matmul<false, true>(s.C, s.B, s.A, k, ldm);      // X inv(R)'
     __syncthreads();
-    matmul<false, false>(s.D, s.A, s.C, k);     // inv(R) X inv(R)'
+    matmul<false, false>(s.D, s.A, s.C, k, ldm);     // inv(R) X inv(R)'
     __syncthreads();
     for (int e = threadIdx.x; e < k * k; e += NT) {
       const int i = e % k, c = e / k;
@@ -478,11 +502,14 @@ int set_attrs() {
   for (int i = 0; i < 6; ++i) CIP_TRY(ensure_dyn_smem(fn[i], SDP_SMEM, &g_attr[i]));
   return 0;
 }
-SDesc sdesc(const ConeDesc& c) { return SDesc{c.slist, c.off, c.sord, c.roff}; }
+SDesc sdesc(const ConeDesc& c) { return SDesc{c.slist, c.off, c.sord, c.roff, c.sws, c.sws_stride}; }
 
 }  // namespace
 
-int sdp_max_order() { return KMAX; }
+int sdp_max_order() { return KCAP; }
+// doubles of global workspace one CTA needs for an S cone of order k (0 up to KMAX: shared memory only)
+long long sdp_workspace_doubles(int k) { return k <= KMAX ? 0 : 4LL * k * (k + 1) + k + 8; }
+int sdp_panel_chunks(int max_order, int ncols) { return max_order <= KMAX ? (ncols + 15) / 16 : std::min(32, (ncols + 15) / 16); }
 
 int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, const double* x, double* y,
               cudaStream_t st) {
@@ -539,8 +566,9 @@ int sdp_scale_panel(const ConeDesc& c, const Scaling& Fi, const double* At4, dou
                     cudaStream_t st) {
   if (c.ns == 0) return 0;
   CIP_TRY(set_attrs());
-  const int per = 16;
-  dim3 grid(c.ns, (ncols + per - 1) / per);
+  const int chunks = sdp_panel_chunks(c.max_s_ord, ncols);
+  const int per = (ncols + chunks - 1) / chunks;
+  dim3 grid(c.ns, chunks);
   sdp_scale_panel_kernel<<<grid, NT, SDP_SMEM, st>>>(sdesc(c), Fi.kind, Fi.Ri, At4, Atil4, ld, ncols, per);
   CIP_CHECK_LAUNCH();
   return 0;

@@ -170,8 +170,10 @@ def test_c5_shaped_lp_with_s64_block_matches_oracle():
     of its solvers, its mu trace alternating between long and short steps over the last ten, and the device path
     -- same algorithm, different rounding in the factorisation -- lands in 26 to 29 depending on the Cholesky
     schedule (scripts/c5_iters.py; independent of the equality-block augmentation).  The +-1 window of the
-    well-conditioned configurations (C1-C3, every other S-cone test) is therefore widened to 3 here; the solution,
-    the objective and the residuals are held to the same tolerances as everywhere else."""
+    well-conditioned configurations (C1-C3, every other S-cone test) is therefore widened to 3 here.  The primal
+    solution and the objective are compared with the oracle's; the dual optimum of a degenerate LP is a face, not
+    a point (two trajectories stop at different points of it: rel(v) ~ 1e-3 at mu = 1e-8), so (v, w) are checked
+    through the optimality conditions themselves, evaluated on the host."""
     import conicip_b200 as cb
     import oracle as O
     prob = P.config5(n=2200, k=64, p=60)
@@ -182,5 +184,15 @@ def test_c5_shaped_lp_with_s64_block_matches_oracle():
     assert s.status == so.status == "Optimal", (s.status, so.status)
     assert abs(s.Iter - so.Iter) <= 3, (s.Iter, so.Iter)
     assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8
-    assert _rel(s.y, so.y) < 1e-5 and _rel(s.v, so.v) < 1e-5, (_rel(s.y, so.y), _rel(s.v, so.v))
+    assert _rel(s.y, so.y) < 1e-5, _rel(s.y, so.y)
     assert abs(s.pobj - so.pobj) <= 1e-7 * (1 + abs(so.pobj))
+    A, G, c, b = prob["A"], prob["G"], prob["c"], prob["b"]
+    n = len(c)
+    stat = G.T @ s.w - A.T @ s.v - c                                  # Q = 0: stationarity of src/ConicIP.jl:747,753
+    assert np.linalg.norm(stat) <= 1e-7 * (1 + np.linalg.norm(c))
+    slack = A @ s.y - b
+    assert s.v[:n].min() > -1e-9 and slack[:n].min() > -1e-7           # R rows: v >= 0, Ay - b >= 0
+    assert np.linalg.eigvalsh(O.mat(s.v[n:])).min() > -1e-9            # S block: mat(v) and mat(Ay - b) PSD
+    assert np.linalg.eigvalsh(O.mat(slack[n:])).min() > -1e-7
+    assert abs(slack @ s.v) <= 1e-6 * (1 + abs(so.pobj))               # complementarity
+    assert np.linalg.norm(G @ s.y - prob["d"]) <= 1e-8 * (1 + np.linalg.norm(prob["d"]))

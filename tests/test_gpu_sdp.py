@@ -23,7 +23,7 @@ def rand_pd(rng, k, cond=10.0):
     return (Qm * np.geomspace(1.0, cond, k)) @ Qm.T
 
 
-@pytest.fixture(scope="module", params=[2, 6, 17, 64])
+@pytest.fixture(scope="module", params=[2, 6, 17, 64, 65, 100])   # 65, 100: above the shared-memory orders
 def scase(request):
     import conicip_b200 as cb
     k = request.param
@@ -180,6 +180,30 @@ def test_mixed_r_q_s_problem_vs_oracle():
 
 def test_s_cone_order_limit_is_loud():
     import conicip_b200 as cb
-    k = 65
+    k = 513
     with pytest.raises(cb.CipError):
         cb.Engine(np.eye(2), np.zeros((k * (k + 1) // 2, 2)), None, [("S", k * (k + 1) // 2)])
+
+
+def test_large_order_s_cone_solve_vs_oracle():
+    """An S cone of order 80 (above the 64 that fit shared memory: the global-workspace path of sdp.cu) through a
+    whole solve: projection of a symmetric matrix onto the PSD cone, as the reference's SDP test does at order 6
+    (runtests.jl:527-552), plus R rows and an equality block."""
+    import conicip_b200 as cb
+    rng = np.random.default_rng(80)
+    k = 80
+    dim = k * (k + 1) // 2
+    B = rng.standard_normal((k, k))
+    target = O.vecm((B + B.T) / 2)
+    n = dim
+    cones = [("S", dim), ("R", 10)]
+    A = np.vstack([np.eye(n), rng.standard_normal((10, n)) / math.sqrt(n)])
+    b = np.concatenate([np.zeros(dim), -np.ones(10)])
+    G = rng.standard_normal((4, n)) / math.sqrt(n)
+    d = G @ O.vecm(np.eye(k))
+    s = cb.conicIP_native(np.eye(n), target, A, b, cones, G, d, optTol=1e-8)
+    so = O.conicIP(np.eye(n), target, A, b, cones, G, d, optTol=1e-8, kktsolver=O.kktsolver_qr)
+    assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1, (s.status, s.Iter, so.Iter)
+    assert rel(s.y, so.y) < 1e-6 and rel(s.v, so.v) < 1e-5
+    assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8
+    assert np.linalg.eigvalsh(O.mat(s.y)).min() > -1e-7

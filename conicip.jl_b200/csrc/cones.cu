@@ -518,7 +518,7 @@ int cone_apply_invsq(const ConeDesc& c, const Scaling& F, const Scaling& Fi, con
     // VecCongurance blocks are not symmetric: inv(R)' first, then inv(R), on the S rows only
     CIP_TRY(sdp_apply(c, F, 1, 1, x, tmp, st));
     CIP_TRY(sdp_apply(c, F, 1, 0, tmp, y, st));
-    if (minus) CIP_TRY(sdp_rows_rsub(c, minus, y, st));
+    if (minus) CIP_TRY(sdp_rows_rsub(c, F, minus, y, st));
   }
   return 0;
 }

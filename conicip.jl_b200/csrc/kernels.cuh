@@ -90,8 +90,8 @@ int sdp_apply(const ConeDesc& c, const Scaling& F, int use_inv, int transpose, c
 int sdp_nt_scaling(const ConeDesc& c, Scaling F, Scaling Fi, const double* v, const double* s, double* lambda,
                    int* info, cudaStream_t st);
 int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st);
-// y = minus - y on the rows of the S cones
-int sdp_rows_rsub(const ConeDesc& c, const double* minus, double* y, cudaStream_t st);
+// y = minus - y on the rows of the S cones that carry a VecCongurance block
+int sdp_rows_rsub(const ConeDesc& c, const Scaling& F, const double* minus, double* y, cudaStream_t st);
 int sdp_prod_div(const ConeDesc& c, const double* x, const double* y, double* o, int divide, cudaStream_t st);
 int sdp_maxstep(const ConeDesc& c, const double* x, const double* d, double d_scale, unsigned long long* key,
                 cudaStream_t st);

@@ -535,15 +535,18 @@ int sdp_invert(const ConeDesc& c, Scaling F, cudaStream_t st) {
   return 0;
 }
 namespace {
-__global__ void sdp_rows_rsub_kernel(SDesc d, const double* __restrict__ minus, double* __restrict__ y) {
+__global__ void sdp_rows_rsub_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ minus,
+                                     double* __restrict__ y) {
   const int si = blockIdx.x, ci = d.slist[si];
+  if (kind[ci] != CIP_BLK_VECCONG) return;      // a Diagonal block on an S cone (F = I at the initial point) was
+                                                // handled, subtraction included, by the elementwise kernel
   const int k = d.sord[si], off = d.off[ci], dim = k * (k + 1) / 2;
   for (int e = threadIdx.x; e < dim; e += blockDim.x) y[off + e] = minus[off + e] - y[off + e];
 }
 }  // namespace
-int sdp_rows_rsub(const ConeDesc& c, const double* minus, double* y, cudaStream_t st) {
+int sdp_rows_rsub(const ConeDesc& c, const Scaling& F, const double* minus, double* y, cudaStream_t st) {
   if (c.ns == 0) return 0;
-  sdp_rows_rsub_kernel<<<c.ns, NT, 0, st>>>(sdesc(c), minus, y);
+  sdp_rows_rsub_kernel<<<c.ns, NT, 0, st>>>(sdesc(c), F.kind, minus, y);
   CIP_CHECK_LAUNCH();
   return 0;
 }

@@ -103,6 +103,25 @@ def test_apply_with_user_supplied_veccongurance(scase):
     assert rel(np.tril(eng.get_H()), np.tril(np.eye(n) + Atil.T @ Atil)) < 1e-10
 
 
+def test_solve_with_diagonal_blocks_on_every_cone(scase):
+    """The initial point of conicIP factors with F = I: a Diagonal block on EVERY cone, S and Q cones included
+    (src/ConicIP.jl:704-706).  The S rows then take the elementwise path of the fused inv(F'F) kernel."""
+    import conicip_b200 as cb
+    eng, k, dim, rng, v, s, A, cones = scase
+    diags = [rng.uniform(0.5, 2.0, kk) for _, kk in cones]
+    F = cb.Block([cb.Diagonal(dg) for dg in diags])
+    Fo = O.Block([O.Diag(dg) for dg in diags])
+    assert eng.factor(F) == 0
+    n = A.shape[1]
+    ry, rv = rng.standard_normal(n), rng.standard_normal(len(v))
+    dy, dw, dv = eng.solve(ry, None, rv)
+    oy, ow, ov = O.kktsolver_qr(np.eye(n), A, np.zeros((0, n)), cones)(Fo, Fo.inv_adjoint())(ry, np.zeros(0), rv)
+    assert rel(dy, oy) < 1e-9 and rel(dv, ov) < 1e-9
+    # the 3x3 system itself: Q dy - A' dv = ry ; A dy + F'F dv = rv   (src/kktsolvers.jl:1-12)
+    d2 = np.concatenate(diags) ** 2
+    assert rel(dy - A.T @ dv, ry) < 1e-9 and rel(A @ dy + d2 * dv, rv) < 1e-9
+
+
 def test_maxstep_sdc(scase):
     eng, k, dim, rng, v, s, A, cones = scase
     d = rng.standard_normal(len(v))

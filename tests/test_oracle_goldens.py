@@ -108,6 +108,18 @@ def test_sdp_projection():
     s = O.conicIP(np.eye(21), c, np.eye(21), np.zeros(21), [("S", 21)], optTol=1e-7)
     assert s.status == "Optimal" and abs(s.Iter - 6) <= 1
     assert np.abs(O.mat(s.y) - np.diag([1.0, 1, 1, 0, 0, 0])).max() < 1e-3
+    # the reference's own acceptance test for this record (`compare`, runtests.jl:15-21: absolute 1e-3 on every field)
+    gold = dict(prFeas=4.2341217602756234e-16, Mu=3.4583513329836624e-10, muFeas=1.48267911727847e-9,
+                duFeas=4.2341217602756234e-16)
+    for k, g in gold.items():
+        assert abs(getattr(s, k) - g) < 1e-3
+    # Why `Mu` itself (3.458e-10 recorded, 6.745e-9 here) is not reproducible from the current source: on the central
+    # path of this problem muFeas / Mu is a constant that depends only on the divisor of `mu = <v,s> / conedim`.
+    # With conedim = ord = 6 (src/ConicIP.jl:551) it is sqrt(1.5) -- what the oracle gives -- while the recorded pair
+    # has sqrt(1.5) * 21/6: the record was made by a version that divided by the vector length 21, i.e. it predates
+    # the source under /root/reference (as the recorded Iter values do).
+    assert abs(s.muFeas / s.Mu - np.sqrt(1.5)) < 1e-6
+    assert abs((gold["muFeas"] / gold["Mu"]) / (s.muFeas / s.Mu) - 21 / 6) < 1e-3
 
 
 def test_solvers_agree_on_mixed_problem():

@@ -10,6 +10,8 @@
 // launches, the NCCL all-reduce of the partial Gram matrices, the block-cyclic Cholesky -- are issued
 // concurrently exactly as the one-process-per-GPU path issues them; the calling thread blocks until every
 // shard has finished, which is the blocking `ccall` semantics the reference protocol expects.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <condition_variable>
@@ -283,7 +285,10 @@ int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq,
   if (As)
     for (int r = 0; r < N; ++r)
       if (slice_csc(As, M->row_lo[r], M->row_hi[r], &slices[r]) != 0) { multi_destroy(h); return -1; }
+  const bool chatty = opts->verbose > 0 || getenv("CIP_VERBOSE");
+  auto say = [&](const char* what) { if (chatty) { fprintf(stderr, "[conicip_b200] multi_create(ngpus=%d): %s\n", N, what); fflush(stderr); } };
   for (int r = 0; r < N; ++r) M->th.emplace_back(&Multi::worker, M, r);
+  say("creating the shard engines");
   int rc = M->run([&](int r) {
     // direct peer copies for slabs that arrive as device pointers on another GPU (ignored where unsupported)
     for (int q = 0; q < N; ++q) {
@@ -308,10 +313,13 @@ int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq,
     return 0;
   });
   if (rc != 0) { multi_destroy(h); return rc; }
+  say("shard engines ready");
   if (N > 1) {
     const NcclApi* api = nccl_api();
     std::vector<void*> comms(N, nullptr);
+    say("ncclCommInitAll");
     const int r = api->CommInitAll(comms.data(), N, M->dev.data());
+    say("ncclCommInitAll done");
     if (r != 0) {
       set_error("ncclCommInitAll failed: %s", api->GetErrorString(r));
       multi_destroy(h);
@@ -320,6 +328,7 @@ int multi_create(cip_handle* out, int n, int m, int p, const double* Q, int ldq,
     for (int q = 0; q < N; ++q) { M->shard[q]->comm = comms[q]; M->shard[q]->nranks = N; M->shard[q]->rank = q; }
     rc = M->run([&](int q) { return engine_setup_comm(M->shard[q]); });
     if (rc != 0) { multi_destroy(h); return rc; }
+    say("communicators attached");
   }
   h->device = M->dev[0];
   *out = h;

@@ -45,5 +45,8 @@ def run(name, n, cone_dims):
     eng.close()
 
 
-run("R", 256, [("R", 1 << 24)])                      # 16.8 M rows: m-vectors 134 MB, A 34 GB
-run("Q33", 256, [("Q", 33)] * ((1 << 24) // 33))     # 508 k second-order cones of dimension 33
+which = sys.argv[1:] or ["R", "Q33"]
+if "R" in which:
+    run("R", 256, [("R", 1 << 24)])                      # 16.8 M rows: m-vectors 134 MB, A 34 GB
+if "Q33" in which:
+    run("Q33", 256, [("Q", 33)] * ((1 << 24) // 33))     # 508 k second-order cones of dimension 33

@@ -399,21 +399,7 @@ maxstep_rq_kernel(int nbR, ConeDesc c, const double* __restrict__ x, const doubl
     const int ci = on ? c.qlist[qi] : 0, off = on ? c.off[ci] : 0, dim = on ? c.off[ci + 1] - off : 0;
     const double* xp = x + off;
     double res;
-    if (!d && G == 8) {                                            // maxstep_soc(x, nothing), :264-270; cone <= 64 rows:
-      double xr[8];                                                // all eight loads of a lane in flight at once
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int i = lid + 8 * e;
-        xr[e] = i < dim ? xp[i] : 0.0;
-      }
-      double nn = 0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) if (lid + 8 * e > 0) nn += xr[e] * xr[e];
-      nn = gsum<G>(nn, sm);
-      const double x0 = __shfl_sync(0xffffffffu, xr[0], threadIdx.x & 24);
-      const double al = sqrt(nn) - (on ? x0 : 1.0);
-      res = al < 0 ? 0.0 : -1.0 - al;
-    } else if (!d) {
+    if (!d) {                                                      // maxstep_soc(x, nothing), :264-270
       double nn = 0;
       for (int i = lid; i < dim; i += G) if (i > 0) nn += xp[i] * xp[i];
       nn = gsum<G>(nn, sm);

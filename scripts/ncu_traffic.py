@@ -45,7 +45,7 @@ def main():
     lines = ["| key | kernel | time | DRAM read | DRAM write | FP64 pipe % of peak (active) | L2 hit % | shared bank conflicts | regs |",
              "|---|---|---|---|---|---|---|---|---|"]
     for a in args:
-        key, f = a.split("=", 1)
+        key, f = a.rsplit("=", 1)
         for d in read_raw(f):
             rd, wr = d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0)
             tab[key] = {"dram_bytes": rd + wr, "source": f"profiles/{os.path.basename(f)} (ncu --set full: dram__bytes_read.sum "

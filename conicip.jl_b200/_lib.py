@@ -76,6 +76,7 @@ SIGNATURES = {
     "cip_factor": (C.c_int, [C.c_void_p, _P, _P, _P, _P, _P]),
     "cip_factor_from_point": (C.c_int, [C.c_void_p, _P, _P, _P]),
     "cip_solve": (C.c_int, [C.c_void_p, _P, _P, _P, _P, _P, _P]),
+    "cip_solve_multi": (C.c_int, [C.c_void_p, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "cip_nt_scaling": (C.c_int, [C.c_void_p, _P, _P, _P]),
     "cip_get_scaling": (C.c_int, [C.c_void_p, _P, _P, _P, _P, _P]),
     "cip_set_scaling": (C.c_int, [C.c_void_p, _P, _P, _P, _P, _P]),

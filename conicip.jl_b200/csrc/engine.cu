@@ -810,6 +810,9 @@ int cip_destroy(cip_handle h) {
   for (auto v : h->nv) if (v) cudaFree(v);
   for (auto v : h->mv) if (v) cudaFree(v);
   for (auto v : h->pv) if (v) cudaFree(v);
+  for (auto v : h->nv2) if (v) cudaFree(v);
+  for (auto v : h->mv2) if (v) cudaFree(v);
+  for (auto v : h->pv2) if (v) cudaFree(v);
   chol_free_plan(&h->cholH);
   chol_free_plan(&h->cholS);
   if (h->Hp) cudaFree(h->Hp);
@@ -1055,6 +1058,109 @@ int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv
     return 0;
   }
   return finish(h);
+}
+
+// Several right-hand sides through one factorisation.  The pivot algebra of cip_solve runs column by column (the
+// sweeps and the cone kernels are per column), but the two products with A -- 2 x 8mn bytes, nine tenths of a
+// solve at config 4 -- are shared by PAIRS of columns: A is streamed once per pair.  Column k of every argument
+// lies at ptr + k * ld.  Replaces `Z\[dy;dw]` / `pivot` applied to several right-hand sides
+// (src/kktsolvers.jl:297-302, :324-332; north_star "the predictor and corrector right-hand sides together").
+int cip_solve_multi(cip_handle h, int nrhs, const double* ry, int ldy, const double* rw, int ldw, const double* rv,
+                    int ldv, double* dy, double* dw, double* dv) {
+  CIP_TRY(check(h));
+  if (nrhs < 0 || (nrhs > 1 && (ldy < h->n || ldv < h->m || (h->p > 0 && ldw < h->p)))) {
+    set_error("cip_solve_multi: bad nrhs / leading dimensions (nrhs=%d ldy=%d ldw=%d ldv=%d)", nrhs, ldy, ldw, ldv);
+    return -1;
+  }
+  auto col = [](const double* p, int k, int ld) { return p ? p + (size_t)k * ld : nullptr; };
+  auto colw = [](double* p, int k, int ld) { return p ? p + (size_t)k * ld : nullptr; };
+  if (h->multi) return multi_solve_multi(h, nrhs, ry, ldy, rw, ldw, rv, ldv, dy, dw, dv);
+  if (!h->have_factor) { set_error("cip_solve_multi before cip_factor"); return -1; }
+  int k = 0;
+  for (; k + 1 < nrhs; k += 2) {
+    if (!h->nv2[0]) {
+      for (auto& v : h->nv2) CIP_TRY(dev_alloc(h, &v, h->n_pad + 4));
+      for (auto& v : h->mv2) CIP_TRY(dev_alloc(h, &v, h->m_pad + 4));
+      for (auto& v : h->pv2) CIP_TRY(dev_alloc(h, &v, h->p_pad + 4));
+    }
+    cudaStream_t s = h->stream;
+    double** NVs[2] = {h->nv, h->nv2};
+    double** MVs[2] = {h->mv, h->mv2};
+    double** PVs[2] = {h->pv, h->pv2};
+    const double *ryp[2], *rvp[2];
+    double* dvp[2];
+    CIP_CUDA(cudaEventRecord(h->ev[6], s));
+    for (int b = 0; b < 2; ++b) {
+      double **nv = NVs[b], **mv = MVs[b], **pv = PVs[b];
+      CIP_TRY(vec_in(h, nv[0], col(ry, k + b, ldy), h->n, &ryp[b]));
+      if (h->p) CIP_TRY(stage_in(h, pv[0], col(rw, k + b, ldw), h->p));
+      CIP_TRY(vec_in(h, mv[0], col(rv, k + b, ldv), h->m, &rvp[b]));
+      double* out = colw(dv, k + b, ldv);
+      dvp[b] = (out != rvp[b]) ? vec_out(h, mv[5], out, h->m) : mv[5];
+      CIP_TRY(cone_apply_invsq(h->cd, h->F, h->Fi, rvp[b], mv[2], nullptr, mv[1], s));          // t1 (:326)
+    }
+    // rhs = y + A' t1 (:327) for both columns in one pass over A
+    if (h->m && !h->comm) {
+      CIP_TRY(q4_mv_rows2(h->nv[2], h->nv2[2], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->mv2[2], h->partial,
+                          h->partial_cap, s, ryp[0], ryp[1]));
+    } else {
+      if (h->m) {
+        CIP_TRY(q4_mv_rows2(h->nv[1], h->nv2[1], h->At4, h->n_pad, h->n, h->m, h->mv[2], h->mv2[2], h->partial,
+                            h->partial_cap, s));
+      } else {
+        CIP_TRY(fill_zero(h->nv[1], h->n, s));
+        CIP_TRY(fill_zero(h->nv2[1], h->n, s));
+      }
+      for (int b = 0; b < 2; ++b) {
+        CIP_TRY(allreduce(h, NVs[b][1], h->n));
+        CIP_TRY(vec_axpby(NVs[b][2], 1.0, ryp[b], 1.0, NVs[b][1], h->n, s));
+      }
+    }
+    for (int b = 0; b < 2; ++b) {
+      double **nv = NVs[b], **pv = PVs[b];
+      if (h->aug_rows > 0) {
+        CIP_TRY(q4_mv_k(nv[4], h->G4, h->p_pad, h->p, h->n, pv[0], s));
+        CIP_TRY(vec_axpby(nv[2], 1.0, nv[2], h->aug_rho, nv[4], h->n, s));
+      }
+      CIP_TRY(chol_fwd(h->cholH, nv[2], nv[3], s));
+      if (h->p) {
+        CIP_TRY(q4_mv_rows(pv[1], h->Z4, h->p_pad, h->p, h->n, nv[3], h->partial, h->partial_cap, s));
+        CIP_TRY(vec_axpby(pv[2], 1.0, pv[1], -1.0, pv[0], h->p, s));
+        CIP_TRY(chol_fwd(h->cholS, pv[2], pv[3], s));
+        CIP_TRY(chol_bwd(h->cholS, pv[3], pv[4], s));
+        CIP_TRY(q4_mv_k(nv[4], h->Z4, h->p_pad, h->p, h->n, pv[4], s));
+        CIP_TRY(vec_axpby(nv[3], 1.0, nv[3], -1.0, nv[4], h->n, s));
+      }
+      CIP_TRY(chol_bwd(h->cholH, nv[3], nv[5], s));
+    }
+    // dv = t1 - F^-T F^-T (A dy) (:328): A dy for both columns in one pass over A
+    if (h->m) {
+      CIP_TRY(q4_mv_k2(h->mv[3], h->mv2[3], h->At4, h->n_pad, h->n, h->m, h->nv[5], h->nv2[5], s));
+      for (int b = 0; b < 2; ++b)
+        CIP_TRY(cone_apply_invsq(h->cd, h->F, h->Fi, MVs[b][3], dvp[b], MVs[b][2], MVs[b][1], s));
+    }
+    CIP_CUDA(cudaEventRecord(h->ev[7], s));
+    for (int b = 0; b < 2; ++b) {
+      CIP_TRY(stage_out(h, colw(dy, k + b, ldy), NVs[b][5], h->n));
+      if (h->p) CIP_TRY(stage_out(h, colw(dw, k + b, ldw), PVs[b][4], h->p));
+      CIP_TRY(vec_out_done(h, colw(dv, k + b, ldv), dvp[b], h->m));
+    }
+    h->st.solves += 2;
+    int bad[2] = {0, 0};
+    if (h->need_sync || h->always_sync) {
+      CIP_CUDA(cudaMemcpyAsync(&bad[0], h->cholH.sweep_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+      if (h->p) CIP_CUDA(cudaMemcpyAsync(&bad[1], h->cholS.sweep_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    CIP_TRY(finish(h));
+    if (bad[0] || bad[1]) {
+      set_error("cip_solve_multi: a triangular sweep gave up waiting for a solution block (internal error)");
+      return -4;
+    }
+  }
+  if (k < nrhs)
+    return cip_solve(h, col(ry, k, ldy), col(rw, k, ldw), col(rv, k, ldv), colw(dy, k, ldy), colw(dw, k, ldw),
+                     colw(dv, k, ldv));
+  return 0;
 }
 
 int cip_solve_H(cip_handle h, const double* rhs, double* x) {

@@ -48,6 +48,11 @@ struct cip_engine {
   double* nv[NV] = {};
   double* mv[MV] = {};
   double* pv[PV] = {};
+  // second set of the work vectors cip_solve uses (nv[0..5], mv[0..5], pv[0..4]): column b of a pair in
+  // cip_solve_multi; allocated on the first call
+  double* nv2[6] = {};
+  double* mv2[6] = {};
+  double* pv2[5] = {};
   double* partial = nullptr;
   int partial_cap = 0;
   double* scalar = nullptr;  // device scratch scalars [8]
@@ -89,6 +94,8 @@ int multi_get_scaling(cip_engine* h, int* kind, double* fa, double* fb, double* 
 int multi_nt_scaling(cip_engine* h, const double* v, const double* s, double* lambda_out, int factor);
 int multi_solve(cip_engine* h, const double* ry, const double* rw, const double* rv, double* dy, double* dw,
                 double* dv);
+int multi_solve_multi(cip_engine* h, int nrhs, const double* ry, int ldy, const double* rw, int ldw, const double* rv,
+                      int ldv, double* dy, double* dw, double* dv);
 int multi_apply(cip_engine* h, int op, const double* x, double* y);
 int multi_maxstep(cip_engine* h, const double* x, const double* d, double d_scale, double* alpha_out);
 int multi_prod_div(cip_engine* h, const double* x, const double* y, double* o, int divide);

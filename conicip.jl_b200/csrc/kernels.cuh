@@ -35,6 +35,12 @@ int q4_mv_rows(double* out, const double* X, int ld, int R, int K, const double*
                int partial_capacity, cudaStream_t s, const double* add = nullptr);
 // out[k] = sum_r X[r,k] u[r]      (warp per k-quad)
 int q4_mv_k(double* out, const double* X, int ld, int R, int K, const double* u, cudaStream_t s);
+// two vectors per pass over X (cip_solve_multi): X is read once; per vector the result equals the one-vector call
+int q4_mv_rows2(double* outa, double* outb, const double* X, int ld, int R, int K, const double* va, const double* vb,
+                double* partial, int partial_capacity, cudaStream_t s, const double* adda = nullptr,
+                const double* addb = nullptr);
+int q4_mv_k2(double* outa, double* outb, const double* X, int ld, int R, int K, const double* ua, const double* ub,
+             cudaStream_t s);
 
 // ---------------------------------------------------------------- cone kernels (cones.cu)
 struct ConeDesc {
@@ -126,6 +132,12 @@ struct CholPlan {
   cudaGraphExec_t graph_exec = nullptr;
   bool capturing = false, graph_failed = false;
   long long graph_kernels = 0;
+  // chol_factor_dist likewise (kernels + NCCL broadcasts), captured on the SECOND call: the first one runs eagerly so
+  // that NCCL has set up its connections before anything is captured
+  cudaGraphExec_t graph_exec_dist = nullptr;
+  bool graph_failed_dist = false;
+  int dist_calls = 0;
+  long long graph_kernels_dist = 0;
   int nranks_hint = 1;      // ranks sharing the factorisation (set by the engine once a communicator exists)
   // persistent triangular sweeps: work units (device), partial sums of split block rows, error flag
   void *units_fwd = nullptr, *units_bwd = nullptr;

@@ -169,6 +169,79 @@ mv_k_kernel(double* __restrict__ out, const double* __restrict__ X, int ld, int 
   }
 }
 
+// ---- two right-hand sides per pass over X (cip_solve_multi): the matrix is streamed ONCE, every element feeds two
+//      accumulator sets.  Same summation order per vector as the single-vector kernels (bit-identical results).
+__global__ void __launch_bounds__(128)
+mv_rows2_kernel(double* __restrict__ partial, const double* __restrict__ X, int ld, int R, int Kq,
+                const double* __restrict__ va, const double* __restrict__ vb, int kq_per_split, int nsplit) {
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  const int split = blockIdx.y;
+  const int q0 = split * kq_per_split;
+  const int q1 = min(Kq, q0 + kq_per_split);
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  if (r < R) {
+    const double* xp = X + ((size_t)q0 * ld + r) * 4;
+    const size_t step = (size_t)ld * 4;
+    int q = q0;
+    for (; q + 1 < q1; q += 2) {
+      const double2 x0 = __ldg(reinterpret_cast<const double2*>(xp));
+      const double2 x1 = __ldg(reinterpret_cast<const double2*>(xp) + 1);
+      const double2 y0 = __ldg(reinterpret_cast<const double2*>(xp + step));
+      const double2 y1 = __ldg(reinterpret_cast<const double2*>(xp + step) + 1);
+      {
+        const double2 v0 = *reinterpret_cast<const double2*>(va + 4 * q), v1 = *reinterpret_cast<const double2*>(va + 4 * q + 2);
+        const double2 w0 = *reinterpret_cast<const double2*>(va + 4 * q + 4), w1 = *reinterpret_cast<const double2*>(va + 4 * q + 6);
+        a0 = fma(x0.x, v0.x, a0); a1 = fma(x0.y, v0.y, a1); a2 = fma(x1.x, v1.x, a2); a3 = fma(x1.y, v1.y, a3);
+        a0 = fma(y0.x, w0.x, a0); a1 = fma(y0.y, w0.y, a1); a2 = fma(y1.x, w1.x, a2); a3 = fma(y1.y, w1.y, a3);
+      }
+      {
+        const double2 v0 = *reinterpret_cast<const double2*>(vb + 4 * q), v1 = *reinterpret_cast<const double2*>(vb + 4 * q + 2);
+        const double2 w0 = *reinterpret_cast<const double2*>(vb + 4 * q + 4), w1 = *reinterpret_cast<const double2*>(vb + 4 * q + 6);
+        b0 = fma(x0.x, v0.x, b0); b1 = fma(x0.y, v0.y, b1); b2 = fma(x1.x, v1.x, b2); b3 = fma(x1.y, v1.y, b3);
+        b0 = fma(y0.x, w0.x, b0); b1 = fma(y0.y, w0.y, b1); b2 = fma(y1.x, w1.x, b2); b3 = fma(y1.y, w1.y, b3);
+      }
+      xp += 2 * step;
+    }
+    for (; q < q1; ++q) {
+      const double2 x0 = __ldg(reinterpret_cast<const double2*>(xp));
+      const double2 x1 = __ldg(reinterpret_cast<const double2*>(xp) + 1);
+      const double2 v0 = *reinterpret_cast<const double2*>(va + 4 * q), v1 = *reinterpret_cast<const double2*>(va + 4 * q + 2);
+      const double2 w0 = *reinterpret_cast<const double2*>(vb + 4 * q), w1 = *reinterpret_cast<const double2*>(vb + 4 * q + 2);
+      a0 = fma(x0.x, v0.x, a0); a1 = fma(x0.y, v0.y, a1); a2 = fma(x1.x, v1.x, a2); a3 = fma(x1.y, v1.y, a3);
+      b0 = fma(x0.x, w0.x, b0); b1 = fma(x0.y, w0.y, b1); b2 = fma(x1.x, w1.x, b2); b3 = fma(x1.y, w1.y, b3);
+      xp += step;
+    }
+    partial[(size_t)split * R + r] = (a0 + a1) + (a2 + a3);
+    partial[((size_t)nsplit + split) * R + r] = (b0 + b1) + (b2 + b3);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mv_k2_kernel(double* __restrict__ outa, double* __restrict__ outb, const double* __restrict__ X, int ld, int R, int K,
+             const double* __restrict__ ua, const double* __restrict__ ub) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kq = blockIdx.x * 8 + warp;
+  if (kq * 4 >= K) return;
+  const double* xp = X + (size_t)kq * ld * 4;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  for (int r = lane; r < R; r += 32) {
+    const double2 x0 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)r * 4));
+    const double2 x1 = __ldg(reinterpret_cast<const double2*>(xp + (size_t)r * 4) + 1);
+    const double ur = ua[r], wr = ub[r];
+    a0 = fma(x0.x, ur, a0); a1 = fma(x0.y, ur, a1); a2 = fma(x1.x, ur, a2); a3 = fma(x1.y, ur, a3);
+    b0 = fma(x0.x, wr, b0); b1 = fma(x0.y, wr, b1); b2 = fma(x1.x, wr, b2); b3 = fma(x1.y, wr, b3);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  b0 = warp_sum(b0); b1 = warp_sum(b1); b2 = warp_sum(b2); b3 = warp_sum(b3);
+  if (lane == 0) {
+    const int k = kq * 4;
+    if (k + 0 < K) { outa[k + 0] = a0; outb[k + 0] = b0; }
+    if (k + 1 < K) { outa[k + 1] = a1; outb[k + 1] = b1; }
+    if (k + 2 < K) { outa[k + 2] = a2; outb[k + 2] = b2; }
+    if (k + 3 < K) { outa[k + 3] = a3; outb[k + 3] = b3; }
+  }
+}
+
 __global__ void axpby_kernel(double* out, double a, const double* x, double b, const double* y, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double r = 0;
@@ -272,6 +345,42 @@ int q4_mv_k(double* out, const double* X, int ld, int R, int K, const double* u,
   if (K <= 0) return 0;
   const int Kq = (K + 3) / 4;
   mv_k_kernel<<<(Kq + 7) / 8, 256, 0, s>>>(out, X, ld, R, K, u);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+int q4_mv_rows2(double* outa, double* outb, const double* X, int ld, int R, int K, const double* va, const double* vb,
+                double* partial, int partial_capacity, cudaStream_t s, const double* adda, const double* addb) {
+  if (R <= 0) return 0;
+  const int Kq = (K + 3) / 4;
+  const int rblocks = (R + 127) / 128;
+  // the same split of the contraction as q4_mv_rows would choose for one vector (so that every column of a pair
+  // gets bit for bit what cip_solve gives it), as long as the partial sums of both vectors fit the buffer
+  int nsplit = (sm_count() * 8 + rblocks - 1) / rblocks;
+  if (nsplit > Kq) nsplit = Kq > 0 ? Kq : 1;
+  if ((long long)nsplit * R > partial_capacity) nsplit = partial_capacity / R;
+  if (2LL * nsplit * R > partial_capacity) nsplit = partial_capacity / (2 * R);
+  if (nsplit < 1) {
+    set_error("q4_mv_rows2: partial buffer too small");
+    return -1;
+  }
+  const int per = (Kq + nsplit - 1) / nsplit;
+  nsplit = per > 0 ? (Kq + per - 1) / per : 1;
+  dim3 grid(rblocks, nsplit);
+  mv_rows2_kernel<<<grid, 128, 0, s>>>(partial, X, ld, R, Kq, va, vb, per, nsplit);
+  CIP_CHECK_LAUNCH();
+  mv_rows_reduce_kernel<<<(R + 255) / 256, 256, 0, s>>>(outa, partial, R, nsplit, adda);
+  CIP_CHECK_LAUNCH();
+  mv_rows_reduce_kernel<<<(R + 255) / 256, 256, 0, s>>>(outb, partial + (size_t)nsplit * R, R, nsplit, addb);
+  CIP_CHECK_LAUNCH();
+  return 0;
+}
+
+int q4_mv_k2(double* outa, double* outb, const double* X, int ld, int R, int K, const double* ua, const double* ub,
+             cudaStream_t s) {
+  if (K <= 0) return 0;
+  const int Kq = (K + 3) / 4;
+  mv_k2_kernel<<<(Kq + 7) / 8, 256, 0, s>>>(outa, outb, X, ld, R, K, ua, ub);
   CIP_CHECK_LAUNCH();
   return 0;
 }

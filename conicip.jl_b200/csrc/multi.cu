@@ -435,6 +435,16 @@ int multi_solve(cip_engine* h, const double* ry, const double* rw, const double*
   });
 }
 
+int multi_solve_multi(cip_engine* h, int nrhs, const double* ry, int ldy, const double* rw, int ldw, const double* rv,
+                      int ldv, double* dy, double* dw, double* dv) {
+  Multi* M = h->multi;
+  return M->run([&](int r) {
+    const long long lo = M->row_lo[r];
+    return cip_solve_multi(M->shard[r], nrhs, ry, ldy, rw, ldw, at(rv, lo), ldv, r == 0 ? dy : nullptr, r == 0 ? dw : nullptr,
+                           at(dv, lo));
+  });
+}
+
 int multi_apply(cip_engine* h, int op, const double* x, double* y) {
   Multi* M = h->multi;
   return M->run([&](int r) { return cip_apply(M->shard[r], op, at(x, M->row_lo[r]), at(y, M->row_lo[r])); });

@@ -7,6 +7,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "../../include/conicip_b200.h"
@@ -458,11 +459,12 @@ sdp_maxstep_kernel(SDesc d, const double* __restrict__ x, const double* __restri
 __global__ void __launch_bounds__(NT)
 sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ Ri,
                        const double* __restrict__ At4, double* __restrict__ Atil4, int ld, int ncols,
-                       int cols_per_cta) {
+                       int cols_per_cta, int skip_up_to) {
   extern __shared__ double smem[];
   const int si = blockIdx.x, ci = d.slist[si];
   if (kind[ci] != CIP_BLK_VECCONG) return;
   const int k = d.sord[si], off = d.off[ci];
+  if (k <= skip_up_to) return;              // done by sdp_scale_panel_dmma_kernel
   SMem s = carve(smem, k, d.ws, d.ws_stride, blockIdx.y * gridDim.x + blockIdx.x);
   const int ldm = s.ldm;
   const int dim = k * (k + 1) / 2;
@@ -494,7 +496,113 @@ sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __re
   (void)dim;
 }
 
+
+// ---- the same panel on the FP64 tensor cores (orders up to KMAX) -------------------------------------------------
+// Per column of A the congruence inv(R) X inv(R)' is two k x k x k products; over the n columns they are two GEMMs
+// with inv(R)' as the shared right operand, [X_1; X_2; ...] inv(R)' and (per column) inv(R) T_j.  A CTA keeps inv(R)
+// resident in shared memory and walks over groups of PCOLS adjacent columns: the group's S rows are staged with
+// coalesced 128-byte runs (in Q4 the PCOLS x 4 doubles of a quad row are contiguous), each column is expanded to the
+// full symmetric matrix, multiplied twice on DMMA.8x8x4 -- warp w owns rows 8w .. 8w+7 of the product, all columns,
+// 16 accumulators per lane -- and packed back into the staging slot, which is written out like it was read.
+// Every k x k array has leading dimension PLD = 68 (= 4 mod 16): the fragment element of lane (g, t) sits at
+// (4s + t) * PLD + row0 + g, sixteen distinct 8-byte banks per half warp, so the LDS.64 are conflict-free.
+// The upper triangle of the product is stored as computed (the scalar kernel averages Y and Y'; the two differ by
+// rounding only).  Replaces `F^-T * Matrix(A)` for VecCongurance blocks, src/kktsolvers.jl:33, src/ConicIP.jl:69.
+constexpr int PLD = 68;
+constexpr int PCOLS = 4;
+constexpr int PANEL_SMEM = (3 * KMAX * PLD + PCOLS * (KMAX * (KMAX + 1) / 2)) * 8;
+static_assert(PANEL_SMEM <= 227 * 1024, "panel kernel shared memory");
+
+__global__ void __launch_bounds__(NT, 1)
+sdp_scale_panel_dmma_kernel(SDesc d, const int* __restrict__ kind, const double* __restrict__ Ri,
+                            const double* __restrict__ At4, double* __restrict__ Atil4, int ld, int ncols) {
+  extern __shared__ double smem[];
+  double* sR = smem;                       // inv(R)      [c * PLD + i] = inv(R)[i][c]
+  double* sX = sR + KMAX * PLD;            // mat(a_j)    [l * PLD + i] = X[i][l]
+  double* sT = sX + KMAX * PLD;            // X inv(R)'   [l * PLD + c] = T[l][c]
+  double* stage = sT + KMAX * PLD;         // PCOLS packed columns, dim doubles each
+  const int si = blockIdx.x, ci = d.slist[si];
+  if (kind[ci] != CIP_BLK_VECCONG) return;
+  const int k = d.sord[si];
+  if (k > KMAX) return;                    // the workspace kernel takes those
+  const int off = d.off[ci], dim = k * (k + 1) / 2;
+  const int kp = (k + 7) & ~7;             // order padded to whole 8 x 8 tiles (zero rows / columns)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const double* src = Ri + d.roff[si];
+  for (int e = tid; e < kp * kp; e += NT) {
+    const int i = e % kp, c = e / kp;
+    sR[c * PLD + i] = (i < k && c < k) ? src[c * k + i] : 0.0;
+    sX[c * PLD + i] = 0.0;                 // the padding stays zero: the expansion below writes i, c < k only
+  }
+  const int groups = (ncols + PCOLS - 1) / PCOLS;
+  const int q0 = off >> 2, nq = ((off + dim - 1) >> 2) - q0 + 1;     // quad rows that hold the block
+  const bool active = warp * 8 < kp;
+  for (int grp = blockIdx.y; grp < groups; grp += gridDim.y) {
+    const int j0 = grp * PCOLS;
+    __syncthreads();                       // the previous group has left the staging buffer
+    for (int idx = tid; idx < nq * 16; idx += NT) {
+      const int quad = q0 + (idx >> 4), c = (idx & 15) >> 2, r = idx & 3;
+      const int e = quad * 4 + r - off;
+      if (e >= 0 && e < dim) stage[c * dim + e] = At4[((size_t)quad * ld + j0 + c) * 4 + r];   // (columns < ld always exist)
+    }
+    __syncthreads();
+    for (int c = 0; c < PCOLS && j0 + c < ncols; ++c) {
+      double* sv = stage + c * dim;
+      for (int e = tid; e < k * k; e += NT) {                       // X = mat(a_j)
+        const int i = e % k, cc = e / k;
+        const int a = i < cc ? i : cc, b = i < cc ? cc : i;
+        const double v = sv[svec_index(a, b, k)];
+        sX[cc * PLD + i] = (i == cc) ? v : v * (1.0 / SQRT2);
+      }
+      __syncthreads();
+      if (active) {                                                 // T = X inv(R)'
+        double acc[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        for (int s4 = 0; s4 < kp / 4; ++s4) {
+          const double a = sX[(4 * s4 + t) * PLD + 8 * warp + g];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            if (nt * 8 < kp) dmma884(acc[nt][0], acc[nt][1], a, sR[(4 * s4 + t) * PLD + nt * 8 + g]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          if (nt * 8 < kp)
+            *reinterpret_cast<double2*>(sT + (8 * warp + g) * PLD + nt * 8 + 2 * t) = make_double2(acc[nt][0], acc[nt][1]);
+      }
+      __syncthreads();
+      if (active) {                                                 // Y = inv(R) T, packed into the column's slot
+        double acc[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+        for (int s4 = 0; s4 < kp / 4; ++s4) {
+          const double a = sR[(4 * s4 + t) * PLD + 8 * warp + g];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            if (nt * 8 < kp) dmma884(acc[nt][0], acc[nt][1], a, sT[(4 * s4 + t) * PLD + nt * 8 + g]);
+        }
+        const int i = 8 * warp + g;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int cc = nt * 8 + 2 * t + u;
+            if (i < k && cc < k && i <= cc) sv[svec_index(i, cc, k)] = (i == cc) ? acc[nt][u] : acc[nt][u] * SQRT2;
+          }
+        }
+      }
+      __syncthreads();                                              // sX and sT are rewritten for the next column
+    }
+    for (int idx = tid; idx < nq * 16; idx += NT) {
+      const int quad = q0 + (idx >> 4), c = (idx & 15) >> 2, r = idx & 3;
+      const int e = quad * 4 + r - off;
+      if (e >= 0 && e < dim && j0 + c < ncols) Atil4[((size_t)quad * ld + j0 + c) * 4 + r] = stage[c * dim + e];
+    }
+  }
+}
+
 std::atomic<unsigned long long> g_attr[6];
+std::atomic<unsigned long long> g_attr_panel{0};
 int set_attrs() {
   const void* fn[6] = {(const void*)sdp_apply_kernel, (const void*)sdp_nt_kernel, (const void*)sdp_invert_kernel,
                        (const void*)sdp_prod_div_kernel, (const void*)sdp_maxstep_kernel,
@@ -569,10 +677,24 @@ int sdp_scale_panel(const ConeDesc& c, const Scaling& Fi, const double* At4, dou
                     cudaStream_t st) {
   if (c.ns == 0) return 0;
   CIP_TRY(set_attrs());
+  // orders up to KMAX: tensor-core kernel (one CTA per SM, inv(R) resident, a loop over groups of PCOLS columns);
+  // larger orders (and CIP_SDP_PANEL_DMMA=0, the A/B switch): the scalar kernel on shared memory / the workspace
+  static const bool use_dmma = [] { const char* e = getenv("CIP_SDP_PANEL_DMMA"); return !e || atoi(e) != 0; }();
+  int skip_up_to = 0;
+  if (use_dmma) {
+    CIP_TRY(ensure_dyn_smem((const void*)sdp_scale_panel_dmma_kernel, PANEL_SMEM, &g_attr_panel));
+    const int groups = (ncols + PCOLS - 1) / PCOLS;
+    const int per_cone = std::max(1, (sm_count() + c.ns - 1) / c.ns);
+    dim3 grid(c.ns, std::min(groups, per_cone));
+    sdp_scale_panel_dmma_kernel<<<grid, NT, PANEL_SMEM, st>>>(sdesc(c), Fi.kind, Fi.Ri, At4, Atil4, ld, ncols);
+    CIP_CHECK_LAUNCH();
+    skip_up_to = KMAX;
+    if (c.max_s_ord <= KMAX) return 0;
+  }
   const int chunks = sdp_panel_chunks(c.max_s_ord, ncols);
   const int per = (ncols + chunks - 1) / chunks;
   dim3 grid(c.ns, chunks);
-  sdp_scale_panel_kernel<<<grid, NT, SDP_SMEM, st>>>(sdesc(c), Fi.kind, Fi.Ri, At4, Atil4, ld, ncols, per);
+  sdp_scale_panel_kernel<<<grid, NT, SDP_SMEM, st>>>(sdesc(c), Fi.kind, Fi.Ri, At4, Atil4, ld, ncols, per, skip_up_to);
   CIP_CHECK_LAUNCH();
   return 0;
 }

@@ -276,6 +276,42 @@ class Engine:
                               self._ptr(dw, self.p) if self.p else None, self._ptr(dv, self.m)))
         return dy, dw, dv
 
+    def solve_multi(self, RY, RW, RV):
+        """`cip_solve_multi`: the columns of RY (n x k), RW (p x k or None), RV (m x k) through the current
+        factorisation; A is streamed once per pair of columns.  Column-major (Fortran-ordered NumPy arrays or
+        transposed torch tensors) -- column j of the result equals `solve(RY[:, j], RW[:, j], RV[:, j])`."""
+        dev = _is_torch(RY) or _is_torch(RV)
+        k = int(RY.shape[1])
+        if dev:
+            self._bind_stream()
+            t = self._torch
+
+            def cols(X, rows):            # (rows x k) -> k contiguous columns: a (k, rows) row-major tensor
+                if X is None:
+                    return None
+                X = X if _is_torch(X) else t.as_tensor(np.asarray(X, dtype=np.float64)).cuda()
+                Xt = X.t().contiguous()
+                assert Xt.shape == (k, rows)
+                return Xt
+            ry, rw, rv = cols(RY, self.n), cols(RW, self.p) if self.p else None, cols(RV, self.m)
+            dy = t.empty((k, self.n), dtype=t.float64, device="cuda")
+            dw = t.empty((k, self.p), dtype=t.float64, device="cuda")
+            dv = t.empty((k, self.m), dtype=t.float64, device="cuda")
+            ptr = lambda x: None if x is None else x.data_ptr()
+        else:
+            def cols(X, rows):
+                if X is None:
+                    return None
+                Xt = np.ascontiguousarray(np.asarray(X, dtype=np.float64).T)
+                assert Xt.shape == (k, rows)
+                return Xt
+            ry, rw, rv = cols(RY, self.n), cols(RW, self.p) if self.p else None, cols(RV, self.m)
+            dy, dw, dv = np.empty((k, self.n)), np.empty((k, self.p)), np.empty((k, self.m))
+            ptr = lambda x: None if x is None else x.ctypes.data
+        check(lib().cip_solve_multi(self._h, k, ptr(ry), self.n, ptr(rw) if self.p else None, max(self.p, 1),
+                                    ptr(rv), self.m, ptr(dy), ptr(dw) if self.p else None, ptr(dv)))
+        return dy.T, dw.T, dv.T
+
     def solve_H(self, rhs):
         """x = inv(H) rhs through the two triangular sweeps alone (`cip_solve_H`, test / bench hook)."""
         dev, (rhs,) = self._prep(rhs)

@@ -156,6 +156,23 @@ function kktsolver_b200(Q, A, G, cone_dims; engine_options...)
     end
     return solve3x3gen
 end
+
+"""
+    solve_multi(eng, Y, W, V) -> (A, B, C)
+
+Several right-hand sides (the columns of `Y` n x k, `W` p x k, `V` m x k) through the current factorisation of
+`eng` in one `ccall` (`cip_solve_multi`): the two products with `A` are shared by pairs of columns.  `conicIP`
+itself cannot use it (its corrector right-hand side depends on the predictor's solution, src/ConicIP.jl:879-907);
+it is for callers with independent right-hand sides.
+"""
+function solve_multi(eng, Y::Matrix{Float64}, W::Matrix{Float64}, V::Matrix{Float64})
+    k = size(Y, 2)
+    A = Matrix{Float64}(undef, eng.n, k); B = Matrix{Float64}(undef, eng.p, k); C = Matrix{Float64}(undef, eng.m, k)
+    check(ccall((:cip_solve_multi, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                eng.h, k, Y, eng.n, W, max(eng.p, 1), V, eng.m, A, B, C))
+    return (A, B, C)
+end
 """
     kktsolver_b200(; ngpus = 8, ...) -> kktsolver
 

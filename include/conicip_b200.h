@@ -151,6 +151,16 @@ int cip_factor_from_point(cip_handle h, const double* v, const double* s, double
 int cip_solve(cip_handle h, const double* ry, const double* rw, const double* rv,
               double* dy, double* dw, double* dv);
 
+/* Several right-hand sides through the current factorisation (BASELINE north_star: "forward/back triangular solves
+ * for the predictor and corrector right-hand sides together"; the reference solves them one `solve3x3` call at a
+ * time, src/ConicIP.jl:688,:879,:907,:919 through src/kktsolvers.jl:297-302,:324-332).  Column k of every argument
+ * lies at ptr + k*ld (ldy >= n, ldw >= p, ldv >= m); column k of the result equals cip_solve on column k.  The
+ * two products with A are shared by pairs of columns (A is streamed once per pair), the rest runs per column.
+ * In conicIP itself the corrector's right-hand side depends on the predictor's solution (src/ConicIP.jl:879-907),
+ * so the stock loop cannot batch them; callers with independent right-hand sides can. */
+int cip_solve_multi(cip_handle h, int nrhs, const double* ry, int ldy, const double* rw, int ldw,
+                    const double* rv, int ldv, double* dy, double* dw, double* dv);
+
 /* ---------------------------------------------------------------- cone kernels
  * The reference has no callback for these (closures over private functions,
  * src/ConicIP.jl:571-665); they are exported so the host driver can keep all

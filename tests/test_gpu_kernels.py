@@ -183,6 +183,34 @@ def test_form_H_cholesky_and_solve(case):
         assert np.linalg.norm(G @ dy - rw) < 1e-10 * scale
 
 
+def test_solve_multi_equals_column_by_column(case):
+    """cip_solve_multi (north_star: the right-hand sides "together"): every column equals cip_solve on that column --
+    bit for bit here, where the shared passes over A use the same split of the contraction -- for an odd count
+    (pairs + a single), with host arrays and with device-resident tensors."""
+    import torch
+    prob, eng, rng, v, s = case
+    n, m, p = len(prob["c"]), prob["A"].shape[0], prob["G"].shape[0]
+    eng.nt_scaling(v, s)
+    eng.factor_resident()
+    k = 5
+    RY, RW, RV = rng.standard_normal((n, k)), rng.standard_normal((p, k)), rng.standard_normal((m, k))
+    DY, DW, DV = eng.solve_multi(RY, RW if p else None, RV)
+    assert DY.shape == (n, k) and DV.shape == (m, k)
+    for j in range(k):
+        dy, dw, dv = eng.solve(RY[:, j], RW[:, j], RV[:, j])
+        assert rel(DY[:, j], dy) < 1e-13 and rel(DV[:, j], dv) < 1e-13
+        if p:
+            assert rel(DW[:, j], dw) < 1e-12
+    tY, tW, tV = (torch.as_tensor(X).cuda() for X in (RY, RW, RV))
+    gY, gW, gV = eng.solve_multi(tY, tW if p else None, tV)
+    assert rel(gY.cpu().numpy(), DY) < 1e-13 and rel(gV.cpu().numpy(), DV) < 1e-13
+    # one column and zero columns are legal
+    Y1, W1, V1 = eng.solve_multi(RY[:, :1], RW[:, :1] if p else None, RV[:, :1])
+    assert rel(Y1[:, 0], DY[:, 0]) < 1e-13
+    Y0, _, V0 = eng.solve_multi(RY[:, :0], RW[:, :0] if p else None, RV[:, :0])
+    assert Y0.shape == (n, 0) and V0.shape == (m, 0)
+
+
 def test_factor_with_host_block_equals_resident(case):
     """cip_factor(flattened Block) == nt_scaling on the device + factor; and the initial
     all-Diagonal(ones) call of src/ConicIP.jl:704 works for Q slots too."""

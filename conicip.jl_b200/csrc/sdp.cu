@@ -510,7 +510,7 @@ sdp_scale_panel_kernel(SDesc d, const int* __restrict__ kind, const double* __re
 // rounding only).  Replaces `F^-T * Matrix(A)` for VecCongurance blocks, src/kktsolvers.jl:33, src/ConicIP.jl:69.
 constexpr int PLD = 68;
 constexpr int PCOLS = 4;
-constexpr int PANEL_SMEM = (3 * KMAX * PLD + PCOLS * (KMAX * (KMAX + 1) / 2)) * 8;
+constexpr int PANEL_SMEM = (3 * KMAX * PLD + PCOLS * (KMAX * (KMAX + 1) / 2 + 16)) * 8;
 static_assert(PANEL_SMEM <= 227 * 1024, "panel kernel shared memory");
 
 __global__ void __launch_bounds__(NT, 1)
@@ -520,13 +520,16 @@ sdp_scale_panel_dmma_kernel(SDesc d, const int* __restrict__ kind, const double*
   double* sR = smem;                       // inv(R)      [c * PLD + i] = inv(R)[i][c]
   double* sX = sR + KMAX * PLD;            // mat(a_j)    [l * PLD + i] = X[i][l]
   double* sT = sX + KMAX * PLD;            // X inv(R)'   [l * PLD + c] = T[l][c]
-  double* stage = sT + KMAX * PLD;         // PCOLS packed columns, dim doubles each
+  double* stage = sT + KMAX * PLD;         // PCOLS packed columns, `sstr` doubles apart
   const int si = blockIdx.x, ci = d.slist[si];
   if (kind[ci] != CIP_BLK_VECCONG) return;
   const int k = d.sord[si];
   if (k > KMAX) return;                    // the workspace kernel takes those
   const int off = d.off[ci], dim = k * (k + 1) / 2;
   const int kp = (k + 7) & ~7;             // order padded to whole 8 x 8 tiles (zero rows / columns)
+  // distance between the staged columns = 4 mod 16: the 4 columns x 4 rows of a quad row (16 consecutive threads of the
+  // coalesced gather / scatter) then fall into 16 different 8-byte banks
+  const int sstr = ((dim + 11) & ~15) + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const double* src = Ri + d.roff[si];
   for (int e = tid; e < kp * kp; e += NT) {
@@ -543,11 +546,11 @@ sdp_scale_panel_dmma_kernel(SDesc d, const int* __restrict__ kind, const double*
     for (int idx = tid; idx < nq * 16; idx += NT) {
       const int quad = q0 + (idx >> 4), c = (idx & 15) >> 2, r = idx & 3;
       const int e = quad * 4 + r - off;
-      if (e >= 0 && e < dim) stage[c * dim + e] = At4[((size_t)quad * ld + j0 + c) * 4 + r];   // (columns < ld always exist)
+      if (e >= 0 && e < dim) stage[c * sstr + e] = At4[((size_t)quad * ld + j0 + c) * 4 + r];   // (columns < ld always exist)
     }
     __syncthreads();
     for (int c = 0; c < PCOLS && j0 + c < ncols; ++c) {
-      double* sv = stage + c * dim;
+      double* sv = stage + c * sstr;
       for (int e = tid; e < k * k; e += NT) {                       // X = mat(a_j)
         const int i = e % k, cc = e / k;
         const int a = i < cc ? i : cc, b = i < cc ? cc : i;
@@ -596,7 +599,7 @@ sdp_scale_panel_dmma_kernel(SDesc d, const int* __restrict__ kind, const double*
     for (int idx = tid; idx < nq * 16; idx += NT) {
       const int quad = q0 + (idx >> 4), c = (idx & 15) >> 2, r = idx & 3;
       const int e = quad * 4 + r - off;
-      if (e >= 0 && e < dim && j0 + c < ncols) Atil4[((size_t)quad * ld + j0 + c) * 4 + r] = stage[c * dim + e];
+      if (e >= 0 && e < dim && j0 + c < ncols) Atil4[((size_t)quad * ld + j0 + c) * 4 + r] = stage[c * sstr + e];
     }
   }
 }

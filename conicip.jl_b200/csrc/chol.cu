@@ -948,8 +948,6 @@ void chol_free_plan(CholPlan* p) {
   if (p->sc) cudaStreamDestroy(p->sc);
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   p->graph_exec = nullptr;
-  if (p->graph_exec_dist) cudaGraphExecDestroy(p->graph_exec_dist);
-  p->graph_exec_dist = nullptr;
   if (p->sd) cudaStreamDestroy(p->sd);
   if (p->se) cudaStreamDestroy(p->se);
   if (p->sf) cudaStreamDestroy(p->sf);
@@ -1171,41 +1169,9 @@ int chol_factor(const CholPlan& p, cudaStream_t s) {
 // per outer panel.  Every tile therefore receives the same sequence of updates as in chol_factor and the factor
 // is bit-identical to the single-GPU one.
 int chol_factor_dist(const CholPlan& p, cudaStream_t s, const CholDist& d) {
-  // Like chol_factor, the launch sequence of a rank is static (kernels, NCCL broadcasts, fork / join pattern), and
-  // with ~20 stream operations per 128-column panel the issuing host thread, not the device, paces the panel chain.
-  // From the second call on it is replayed as a CUDA graph (NCCL collectives are capturable; the first call runs
-  // eagerly so that NCCL's lazy connection set-up never happens under capture).  CIP_CHOL_DIST_GRAPH=0 disables it.
-  static const bool use_graph = [] { const char* e = getenv("CIP_CHOL_DIST_GRAPH"); return !e || atoi(e) != 0; }();
-  CholPlan& mp = const_cast<CholPlan&>(p);
-  if (use_graph && !p.capturing) {
-    if (!mp.graph_exec_dist && !mp.graph_failed_dist && mp.dist_calls >= 1) {
-      cudaGraph_t g = nullptr;
-      mp.capturing = true;
-      const long long before = g_launches.load();
-      cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
-      int rc = -1;
-      if (e == cudaSuccess) {
-        rc = chol_factor_dist(p, s, d);
-        e = cudaStreamEndCapture(s, &g);
-      }
-      mp.capturing = false;
-      mp.graph_kernels_dist = g_launches.load() - before;
-      if (e == cudaSuccess && rc == 0 && g) e = cudaGraphInstantiate(&mp.graph_exec_dist, g, 0);
-      if (g) cudaGraphDestroy(g);
-      if (e != cudaSuccess || rc != 0 || !mp.graph_exec_dist) {
-        cudaGetLastError();
-        mp.graph_exec_dist = nullptr;
-        mp.graph_failed_dist = true;              // plain stream launches for this plan from now on
-        if (getenv("CIP_VERBOSE")) fprintf(stderr, "[conicip_b200] distributed Cholesky: graph capture failed (%s), staying eager\n", cudaGetErrorString(e));
-      }
-    }
-    if (mp.graph_exec_dist) {
-      CIP_CUDA(cudaGraphLaunch(mp.graph_exec_dist, s));
-      g_launches += mp.graph_kernels_dist;
-      return 0;
-    }
-  }
-  if (!p.capturing) mp.dist_calls++;
+  // (Replaying this sequence as a CUDA graph, as chol_factor does, was tried in round 2: capturing the NCCL broadcasts
+  //  fails with "operation not permitted when stream is capturing" under NCCL 2.28 and leaves a single-process handle
+  //  hung, so the distributed variant stays on plain stream launches.)
   int OUTER = 4;
   if (const char* env = getenv("CIP_CHOL_OUTER")) { const int v = atoi(env); if (v >= 1 && v <= 8) OUTER = v; }
   const NcclApi* api = nccl_api();

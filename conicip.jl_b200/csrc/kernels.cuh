@@ -132,12 +132,6 @@ struct CholPlan {
   cudaGraphExec_t graph_exec = nullptr;
   bool capturing = false, graph_failed = false;
   long long graph_kernels = 0;
-  // chol_factor_dist likewise (kernels + NCCL broadcasts), captured on the SECOND call: the first one runs eagerly so
-  // that NCCL has set up its connections before anything is captured
-  cudaGraphExec_t graph_exec_dist = nullptr;
-  bool graph_failed_dist = false;
-  int dist_calls = 0;
-  long long graph_kernels_dist = 0;
   int nranks_hint = 1;      // ranks sharing the factorisation (set by the engine once a communicator exists)
   // persistent triangular sweeps: work units (device), partial sums of split block rows, error flag
   void *units_fwd = nullptr, *units_bwd = nullptr;

@@ -69,6 +69,12 @@ def test_single_process_multi_gpu_handle_matches_one_device():
         assert rel(np.tril(e2.get_H()), np.tril(e1.get_H())) < 1e-11
         (dy1, dw1, dv1), (dy2, dw2, dv2) = e1.solve(ry, rw, rv), e2.solve(ry, rw, rv)
         assert rel(dy2, dy1) < 1e-9 and rel(dv2, dv1) < 1e-9 and (p == 0 or rel(dw2, dw1) < 1e-9)
+        # several right-hand sides at once through the sharded handle (cip_solve_multi: global columns in and out)
+        RY, RW, RV = rng.standard_normal((n, 3)), rng.standard_normal((p, 3)), rng.standard_normal((m, 3))
+        MY, MW, MV = e2.solve_multi(RY, RW if p else None, RV)
+        for j in range(3):
+            sy, sw, sv = e1.solve(RY[:, j], RW[:, j], RV[:, j])
+            assert rel(MY[:, j], sy) < 1e-9 and rel(MV[:, j], sv) < 1e-9 and (p == 0 or rel(MW[:, j], sw) < 1e-9)
         x = rng.standard_normal(m)
         for op in (cb.OP_F, cb.OP_FT, cb.OP_FINVT, cb.OP_FINV):
             assert rel(e2.apply(op, x), e1.apply(op, x)) < 1e-13

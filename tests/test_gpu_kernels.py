@@ -75,10 +75,39 @@ CASES = {
 }
 
 
+# heterogeneous cone lists: the fused R+Q kernels pick the lanes-per-cone class (8 / 32 / 256) from the LARGEST Q cone
+# of the problem, so small cones also run in the wider classes; dimensions sit on the class boundaries (64 | 65,
+# 1024 | 1025), R blocks are interleaved with Q cones, and Q cones of dimension 2 (a single tail entry) are included
+CASES["q_class8_edges"] = dict(cones=[("Q", 57), ("R", 1), ("Q", 64), ("Q", 2), ("Q", 8), ("Q", 9), ("R", 3), ("Q", 63)], n=70, p=2, seed=11)
+CASES["q_class32_mixed"] = dict(cones=[("R", 7), ("Q", 2), ("Q", 64), ("Q", 65), ("Q", 3), ("R", 5), ("Q", 200), ("Q", 1024)], n=90, p=0, seed=12)
+CASES["q_class256_mixed"] = dict(cones=[("Q", 5), ("Q", 1025), ("R", 3), ("Q", 33), ("Q", 1024), ("Q", 2)], n=50, p=3, seed=13)
+
+
+def hetero_problem(cones, n, p, seed):
+    """Like problems.mixed, for an arbitrary list of R / Q cones."""
+    rng = np.random.default_rng(seed)
+    m = sum(k for _, k in cones)
+    A = rng.standard_normal((m, n)) / np.sqrt(n)
+    y0 = rng.standard_normal(n)
+    s0, off = np.zeros(m), 0
+    for t, k in cones:
+        if t == "R":
+            s0[off:off + k] = rng.uniform(0.1, 1.1, k)
+        else:
+            u = 0.1 * rng.standard_normal(k - 1)
+            s0[off] = 1.0 + np.linalg.norm(u)
+            s0[off + 1:off + k] = u
+        off += k
+    G = rng.standard_normal((p, n)) / np.sqrt(n)
+    return dict(name="hetero", Q=np.eye(n) * 1.5, c=rng.standard_normal(n), A=A, b=A @ y0 - s0, cone_dims=list(cones),
+                G=G, d=G @ y0, optTol=1e-8)
+
+
 @pytest.fixture(scope="module", params=list(CASES))
 def case(request):
     import conicip_b200 as cb
-    prob = P.mixed(**CASES[request.param])
+    kw = CASES[request.param]
+    prob = hetero_problem(**kw) if "cones" in kw else P.mixed(**kw)
     p = prob["G"].shape[0]
     eng = cb.Engine(prob["Q"], prob["A"], prob["G"] if p else None, prob["cone_dims"])
     rng = np.random.default_rng(123)
@@ -362,3 +391,20 @@ def test_folded_scaling_matches_materialised_panel():
         dy2, _, dv2 = e1.solve(ry, None, rv)
         assert np.linalg.norm(dy2 - dy0) <= 1e-9 * np.linalg.norm(dy0)
         e0.close(); e1.close()
+
+
+@pytest.mark.parametrize("name", ["q_class8_edges", "q_class32_mixed", "q_class256_mixed"])
+def test_heterogeneous_q_cones_full_solve(name):
+    """Whole solves (native loop and host driver) on the heterogeneous cone lists above against the oracle:
+    north_star's gate -- iterations within +-1, y, v, w within 1e-6, residuals below 1e-8."""
+    import conicip_b200 as cb
+    kw = CASES[name]
+    prob = hetero_problem(**kw)
+    Q, c, A, b, cd, G, d = (prob[k] for k in ("Q", "c", "A", "b", "cone_dims", "G", "d"))
+    p = G.shape[0]
+    so = O.conicIP(Q, c, A, b, cd, G if p else None, d if p else None, optTol=1e-8, kktsolver=O.pivot(O.kktsolver_2x2))
+    for solve in (cb.conicIP_native, cb.conicIP):
+        s = solve(Q, c, A, b, cd, G if p else None, d if p else None, optTol=1e-8)
+        assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1, (solve.__name__, s.status, s.Iter, so.Iter)
+        assert rel(s.y, so.y) < 1e-6 and rel(s.v, so.v) < 1e-6 and (p == 0 or rel(s.w, so.w) < 1e-6)
+        assert max(s.prFeas, s.duFeas, s.muFeas) < 1e-8

@@ -43,6 +43,7 @@ CONFIGS = {
     "C2": (8192, 16384, "dense polyhedral QP n={n}, m={m} inequality rows, K=R^m, Q=diag+UU' (rank 32)"),
     "C1": (1000, 1000, "README nonnegative QP n={n}, Q=S'S (S~sprandn 0.1), A=I, K=R^n"),
     "C3": (4096, 16896, "SOCP n={n}, 512 Q-cones of dim 33 (m={m}) + equality block G (p=256)"),
+    "C5": (20000, 22080, "MOI-shaped LP n={n}: x >= 0 plus one S block of order 64 (m={m}), sparse equality block G (p=1000), Q = 0"),
 }
 
 
@@ -160,8 +161,10 @@ def cpu_unit_oracle(prob, pts, rhs, repeats=1):
         for t, k in prob["cone_dims"]:                                               # nt_scaling, src/ConicIP.jl:589-605
             if t == "R":
                 blocks.append(O.Diag(np.sqrt(s[off:off + k] / v[off:off + k])))
-            else:
+            elif t == "Q":
                 blocks.append(O.nestod_soc(v[off:off + k], s[off:off + k]))
+            else:
+                blocks.append(O.nestod_sdc(v[off:off + k], s[off:off + k]))
             off += k
         F = O.Block(blocks)
         solve = gen(F, F.inv_adjoint())
@@ -181,6 +184,8 @@ def host_problem(cfg, n, m):
         prob = P.config1(n=n)
     elif cfg == "C3":
         prob = P.config3(n=n, ncones=m // 33)
+    elif cfg == "C5":
+        prob = P.config5(n=n, k=64, p=1000 if n >= 20000 else max(8, n // 20))
     else:
         rng = np.random.default_rng(2)
         A = rng.standard_normal((m, n)) / math.sqrt(n)
@@ -197,9 +202,14 @@ def host_problem(cfg, n, m):
         for t, k in prob["cone_dims"]:
             if t == "R":
                 v[off:off + k] = rng.uniform(0.5, 1.5, k); s[off:off + k] = rng.uniform(0.5, 1.5, k)
-            else:
+            elif t == "Q":
                 for x in (v, s):
                     u = rng.standard_normal(k - 1); x[off] = np.linalg.norm(u) + 0.5; x[off + 1:off + k] = u
+            else:                                    # S: vecm of a well-conditioned positive definite matrix
+                ks = int(round((math.sqrt(1 + 8 * k) - 1) / 2))
+                for x in (v, s):
+                    B = rng.standard_normal((ks, ks)) / math.sqrt(ks)
+                    x[off:off + k] = P._svec(B @ B.T + 0.5 * np.eye(ks))
             off += k
         return v, s
     pts = [point(), point()]
@@ -477,7 +487,7 @@ def run_b200(args, n, m):
         c_vec, b_loc, d_vec = pr["c"], pr["b"], None
         hprob = None
     else:
-        assert D.world == 1, "C1 / C3 are single-GPU bench lines"
+        assert D.world == 1, "C1 / C3 / C5 are single-GPU bench lines"
         hprob, hpts, hrhs = host_problem(cfg, n, m)
         p = hprob["G"].shape[0]
         eng = cb.Engine(hprob["Q"], hprob["A"], hprob["G"] if p else None, hprob["cone_dims"], ngpus=ngpus_single)
@@ -610,10 +620,11 @@ def run_b200(args, n, m):
                               f"at the real n={n} ({r['t_chol_s']:.1f} s), {NSOLVES}x2 dtrsv ({r['t_trsv_s']:.2f} s); "
                               f"`bench.py --impl reference` measures a larger share")}
         else:
-            t = cpu_unit_oracle(hprob, hpts, hrhs, repeats=2)
+            reps = 1 if cfg == "C5" else 2           # a C5 unit is ~a minute of host time: one warm-up + one timed pass
+            t = cpu_unit_oracle(hprob, hpts, hrhs, repeats=reps)
             cpu = {"value": 1.0 / t, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": False,
                    "measured_fraction": 1.0,
-                   "sample": f"oracle.kktsolver_chol through the 3-level protocol, whole unit, best of 2, {threads} threads"}
+                   "sample": f"oracle.kktsolver_chol through the 3-level protocol, whole unit, best of {reps}, {threads} threads"}
 
     # ---- C2: a second record where the whole unit is measured on both arms (N = 1, default workload only)
     c2 = None

@@ -341,23 +341,34 @@ int factor_H(cip_engine* h) {
   }
   CIP_CUDA(cudaEventRecord(h->ev[4], s));
   if (h->p > 0) {
-    // Z = G L^-T by a right-looking blocked substitution on the DMMA tiles, S = Z Z', S = Ls Ls'
+    // Z = G L^-T by a right-looking blocked substitution on the DMMA tiles, S = Z Z', S = Ls Ls'.
+    // Two-level like the Cholesky: inside an outer panel of four 128-column panels every panel is solved against
+    // inv(L_jj) and applied to the rest of the outer panel only; everything right of the outer panel gets ONE update
+    // with K = 512, which amortises the C-tile read-modify-write that holds K = 128 tiles at a third of the pipe.
     CIP_TRY(vec_copy(h->Z4, h->G4, (size_t)h->p_pad * h->n_pad, s));
     const int np = h->n_pad / TILE, ptiles = h->p_pad / TILE;
-    for (int jb = 0; jb < np; ++jb) {
-      const int j0 = jb * TILE;
+    auto z_trsm = [&](int jb) -> int {                       // Z[:, jb] <- Z[:, jb] inv(L_jj)'
       GemmArgs t{};
       t.lower = 0; t.ntm = ptiles; t.ntn = 1; t.sym = 0;
-      t.x_row0 = 0; t.y_row0 = 0; t.x_kq0 = j0 / 4; t.y_kq0 = 32 * jb; t.nk = TILE / 32;
-      t.Cin = nullptr; t.Cout = h->Z4; t.ldc = h->p_pad; t.c_row0 = 0; t.c_col0 = j0; t.alpha = 1.0;
-      CIP_TRY(launch_gemm_nt(h->mapZ, h->cholH.mapWinv, t, s));
-      const int rem = np - jb - 1;
-      if (rem == 0) break;
+      t.x_row0 = 0; t.y_row0 = 0; t.x_kq0 = jb * TILE / 4; t.y_kq0 = 32 * jb; t.nk = TILE / 32;
+      t.Cin = nullptr; t.Cout = h->Z4; t.ldc = h->p_pad; t.c_row0 = 0; t.c_col0 = jb * TILE; t.alpha = 1.0;
+      return launch_gemm_nt(h->mapZ, h->cholH.mapWinv, t, s);
+    };
+    auto z_update = [&](int k0, int kn, int c0, int cn) -> int {   // Z[:, c0..c0+cn) -= Z[:, k0..k0+kn) L[c0..c0+cn, k0..k0+kn)'   (panel units)
       GemmArgs u{};
-      u.lower = 0; u.ntm = ptiles; u.ntn = rem; u.sym = 0;
-      u.x_row0 = 0; u.y_row0 = j0 + TILE; u.x_kq0 = j0 / 4; u.y_kq0 = j0 / 4; u.nk = TILE / 32;
-      u.Cin = h->Z4; u.Cout = h->Z4; u.ldc = h->p_pad; u.c_row0 = 0; u.c_col0 = j0 + TILE; u.alpha = -1.0;
-      CIP_TRY(launch_gemm_nt(h->mapZ, h->cholH.mapH, u, s));
+      u.lower = 0; u.ntm = ptiles; u.ntn = cn; u.sym = 0;
+      u.x_row0 = 0; u.y_row0 = c0 * TILE; u.x_kq0 = k0 * TILE / 4; u.y_kq0 = k0 * TILE / 4; u.nk = kn * TILE / 32;
+      u.Cin = h->Z4; u.Cout = h->Z4; u.ldc = h->p_pad; u.c_row0 = 0; u.c_col0 = c0 * TILE; u.alpha = -1.0;
+      return launch_gemm_nt(h->mapZ, h->cholH.mapH, u, s);
+    };
+    const int ZOUTER = 4;
+    for (int J0 = 0; J0 < np; J0 += ZOUTER) {
+      const int J1 = std::min(J0 + ZOUTER, np);
+      for (int jb = J0; jb < J1; ++jb) {
+        CIP_TRY(z_trsm(jb));
+        if (jb + 1 < J1) CIP_TRY(z_update(jb, 1, jb + 1, J1 - jb - 1));
+      }
+      if (J1 < np) CIP_TRY(z_update(J0, J1 - J0, J1, np - J1));
     }
     GemmArgs a{};
     a.lower = 1; a.ntm = a.ntn = ptiles; a.sym = 1;

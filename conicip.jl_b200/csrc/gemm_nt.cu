@@ -21,7 +21,7 @@ constexpr int BOX_DOUBLES = HALF * 4 * KQ;       // 2048 doubles
 constexpr int BOX_BYTES = BOX_DOUBLES * 8;       // 16 KB
 constexpr int STAGE_DOUBLES = 4 * BOX_DOUBLES;   // 64 KB
 constexpr int CONSUMER_WARPS = 8;
-constexpr int BAND = 12;
+constexpr int BAND_DEFAULT = 12;      // tile rows per band of the lower-triangular rasterisation (GemmArgs::band; CIP_GEMM_BAND)
 constexpr int NUM_THREADS = (CONSUMER_WARPS + 1) * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128 + STAGES * KT * 8;   // tiles | barriers | k scales per stage
 
@@ -31,8 +31,9 @@ __device__ __forceinline__ void tile_of(const GemmArgs& a, int t, int& ti, int& 
     // Band rasterisation of the lower-triangular tile grid: bands of BAND tile rows, column-major
     // inside a band, so the ~148 concurrently resident CTAs cover ~BAND rows x ~148/BAND columns and
     // share their X / Y panels in L2 (instead of one long row of tiles with 148 distinct Y panels).
+    const int BAND = a.band > 0 ? a.band : BAND_DEFAULT;
     int b = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f) / BAND;
-    auto before = [](int bb) { const long long R = (long long)bb * BAND; return R * (R + 1) / 2; };
+    auto before = [BAND](int bb) { const long long R = (long long)bb * BAND; return R * (R + 1) / 2; };
     while (before(b + 1) <= t) ++b;
     while (before(b) > t) --b;
     const int r0 = b * BAND;
@@ -278,7 +279,16 @@ int make_q4_tensor_map(CUtensorMap* out, const double* base, int ld, long long k
   return 0;
 }
 
-int unpack_tile_major(const GemmArgs& a, cudaStream_t stream) {
+// (A/B knob for the DRAM-traffic experiments of profiles/: the same value must reach every kernel that maps tile
+//  indices -- the GEMM, the split-K reduction and the tile-major unpack)
+static int gemm_band() {
+  static const int v = [] { const char* e = getenv("CIP_GEMM_BAND"); const int x = e ? atoi(e) : 0; return (x >= 1 && x <= 64) ? x : BAND_DEFAULT; }();
+  return v;
+}
+
+int unpack_tile_major(const GemmArgs& a_in, cudaStream_t stream) {
+  GemmArgs a = a_in;
+  a.band = gemm_band();
   const long long all_tiles = a.lower ? (long long)a.ntm * (a.ntm + 1) / 2 : (long long)a.ntm * a.ntn;
   const long long tiles = a.tile_count > 0 ? a.tile_count : all_tiles - a.tile_begin;
   if (tiles <= 0) return 0;
@@ -295,6 +305,7 @@ int launch_gemm_nt(const GemmOperand& X, const GemmOperand& Y, const GemmArgs& a
   const long long tiles = a.tile_count > 0 ? a.tile_count : all_tiles - a.tile_begin;
   if (tiles <= 0 || (a.nk <= 0 && !a.Ctm)) return 0;      // (nk = 0 with tile-major output: the tiles are Cin, or zero)
   GemmArgs b = a;
+  b.band = gemm_band();
   b.ksplit = 1;
   b.kchunk = a.nk;
   b.tail0 = (int)tiles;

@@ -49,6 +49,7 @@ struct GemmArgs {
   // Y tile is lower triangular (Y[j, k] = 0 for k > j, tile-aligned, nk = 4: the inverse of a diagonal block in
   // the Cholesky TRSM): a consumer warp skips the k tiles that only meet zeros of its 32 columns
   int y_lower_tri;
+  int band;            // tile rows per band of the lower-triangular rasterisation (set by launch_gemm_nt)
   // Row scaling folded into the contraction (SYRK of an R-cone problem without a materialised Atil = F^-T A):
   // C += sum_k X[i,k] * kscale[k]^2 * Y[j,k].  The 32 factors of a k tile travel with it through the pipeline (one
   // 256-byte bulk copy per stage) and are applied to the Y fragments in registers.  nullptr: no scaling.

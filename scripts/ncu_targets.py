@@ -2,7 +2,7 @@
 kernel of interest a few times at a named shape and nothing else of note, so that `-k regex:... -c N` picks it:
 
     ncu --set full --clock-control none --import-source on -k regex:gemm_nt -c 2 -o X python scripts/ncu_targets.py syrk_fold
-    targets: syrk_fold (C2 shape, W^-2 folded into the SYRK), syrk (C2 shape, Atil materialised),
+    targets: syrk_fold (C2 shape, W^-2 folded into the SYRK), syrk (C2 shape, Atil materialised), syrk_big (n = 16384, m = 65536),
              sweeps (n = 16384 triangular sweeps), chol (n = 8192 factorisation: potrf_diag / chol_head / updates),
              c5panel (config-5 shaped: S block of order 64 + R rows, scaled panel + cone kernels)"""
 import os
@@ -36,6 +36,12 @@ if target in ("syrk", "syrk_fold"):
     eng.nt_scaling(v, s)
     for _ in range(2):
         eng.form_H()
+elif target == "syrk_big":
+    # n = 16384 with a quarter of config 4's rows: the tile grid, the panel sizes (far beyond L2) and the co-residency
+    # pattern of the C4 SYRK at a quarter of its duration (DRAM traffic scales with m)
+    eng, v, s = r_problem(16384, int(sys.argv[2]) if len(sys.argv) > 2 else 65536, fold_scaling=2)
+    eng.nt_scaling(v, s)
+    eng.form_H()
 elif target == "sweeps":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     eng, v, s = r_problem(n, 2048)

@@ -361,7 +361,9 @@ int factor_H(cip_engine* h) {
       u.Cin = h->Z4; u.Cout = h->Z4; u.ldc = h->p_pad; u.c_row0 = 0; u.c_col0 = c0 * TILE; u.alpha = -1.0;
       return launch_gemm_nt(h->mapZ, h->cholH.mapH, u, s);
     };
-    const int ZOUTER = 4;
+    // (few right-hand-side tiles, p <= 384: every launch is latency-bound and the extra level only lengthens the chain --
+    //  config 3, p = 256: 1.73 ms single-level against 2.07 ms two-level; config 5, p = 1000: 22.0 ms against 35.6 ms)
+    const int ZOUTER = (ptiles >= 4) ? 4 : 1;
     for (int J0 = 0; J0 < np; J0 += ZOUTER) {
       const int J1 = std::min(J0 + ZOUTER, np);
       for (int jb = J0; jb < J1; ++jb) {

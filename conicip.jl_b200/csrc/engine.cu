@@ -308,7 +308,28 @@ int form_H(cip_engine* h) {
     a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES;        // tall-skinny A (n << m): split the contraction
     if (h->fold) a.kscale = h->Fi.a;                          // W^-2 applied to the fragments: no Atil4
     const GemmOperand& op = h->fold ? h->mapAt : h->mapAtil;
-    CIP_TRY(launch_gemm_nt(op, op, a, s));
+    // Long contractions run as several launches over row chunks of A, each accumulating into H.  The tiles of one
+    // launch start in phase (they share their operand panels through L2) but drift apart as they run: at n = 16384
+    // the DRAM re-read factor of A grows from 12.5x (16 k rows per launch) over 15.5x (64 k) to 23.6x (262 k, one
+    // launch; `profiles/r02_syrk_traffic.md`).  A new launch every 64 k rows re-aligns them; it costs one more
+    // read-modify-write of the lower tiles of H (2 GB against ~130 GB of operand traffic) per chunk and no measurable time.
+    static const int kchunk_rows = [] { const char* e = getenv("CIP_SYRK_KCHUNK"); const int v = e ? atoi(e) : 65536; return v > 0 ? (v + 31) / 32 * 32 : 0; }();
+    const int total_kt = k_rows / 32;
+    const int chunk_kt = (kchunk_rows > 0 && h->n_pad >= 4096) ? kchunk_rows / 32 : total_kt;
+    if (total_kt > chunk_kt + chunk_kt / 2) {
+      for (int kt0 = 0; kt0 < total_kt;) {
+        int kn = chunk_kt;
+        if (total_kt - (kt0 + kn) < chunk_kt / 2) kn = total_kt - kt0;       // fold a short remainder into the last chunk
+        GemmArgs c = a;
+        c.x_kq0 = c.y_kq0 = kt0 * 8;
+        c.nk = kn;
+        if (kt0 > 0) c.Cin = h->H4;
+        CIP_TRY(launch_gemm_nt(op, op, c, s));
+        kt0 += kn;
+      }
+    } else {
+      CIP_TRY(launch_gemm_nt(op, op, a, s));
+    }
   } else {
     if (cin) CIP_TRY(vec_copy(h->H4, cin, (size_t)h->n_pad * h->n_pad, s));
     else CIP_TRY(fill_zero(h->H4, (size_t)h->n_pad * h->n_pad, s));

@@ -308,12 +308,10 @@ int form_H(cip_engine* h) {
     a.ws = h->gemm_ws; a.ws_doubles = GEMM_WS_DOUBLES;        // tall-skinny A (n << m): split the contraction
     if (h->fold) a.kscale = h->Fi.a;                          // W^-2 applied to the fragments: no Atil4
     const GemmOperand& op = h->fold ? h->mapAt : h->mapAtil;
-    // Long contractions run as several launches over row chunks of A, each accumulating into H.  The tiles of one
-    // launch start in phase (they share their operand panels through L2) but drift apart as they run: at n = 16384
-    // the DRAM re-read factor of A grows from 12.5x (16 k rows per launch) over 15.5x (64 k) to 23.6x (262 k, one
-    // launch; `profiles/r02_syrk_traffic.md`).  A new launch every 64 k rows re-aligns them; it costs one more
-    // read-modify-write of the lower tiles of H (2 GB against ~130 GB of operand traffic) per chunk and no measurable time.
-    static const int kchunk_rows = [] { const char* e = getenv("CIP_SYRK_KCHUNK"); const int v = e ? atoi(e) : 65536; return v > 0 ? (v + 31) / 32 * 32 : 0; }();
+    // Experiment knob (profiles/r02_syrk_traffic.md): CIP_SYRK_KCHUNK = rows of A per launch, every launch
+    // accumulating into H.  Off by default: at C4 it did not lower the DRAM traffic of the operand panels (994 GB in
+    // four launches against 812 GB in one) and costs 0.1 % of the SYRK time.
+    static const int kchunk_rows = [] { const char* e = getenv("CIP_SYRK_KCHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? (v + 31) / 32 * 32 : 0; }();
     const int total_kt = k_rows / 32;
     const int chunk_kt = (kchunk_rows > 0 && h->n_pad >= 4096) ? kchunk_rows / 32 : total_kt;
     if (total_kt > chunk_kt + chunk_kt / 2) {

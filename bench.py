@@ -584,12 +584,17 @@ def run_b200(args, n, m):
     # ---- full interior-point solve: time-to-1e-8 (native loop: one cip_ipm_solve call per rank)
     solve_info = None
     if not args.no_solve:
-        D.barrier()
-        t0 = time.perf_counter()
-        y, w, vv, info = eng.ipm_solve(c_vec, b_loc, d_vec, optTol=1e-8)
-        D.barrier()
-        t_solve = D.max(time.perf_counter() - t0)
-        solve_info = {"time_to_1e-8_s": t_solve, "status": info["status"], "iterations": info["Iter"],
+        # small configurations: the first call also pays one-time costs (lazy loading of the kernels only the loop uses,
+        # pool allocation), which vary from box to box and dwarf a 10 ms solve -- time a second call and report both
+        t_calls = []
+        for _ in range(1 if cfg == "C4" else 2):
+            D.barrier()
+            t0 = time.perf_counter()
+            y, w, vv, info = eng.ipm_solve(c_vec, b_loc, d_vec, optTol=1e-8)
+            D.barrier()
+            t_calls.append(D.max(time.perf_counter() - t0))
+        t_solve = min(t_calls)
+        solve_info = {"time_to_1e-8_s": t_solve, "first_call_s": t_calls[0], "status": info["status"], "iterations": info["Iter"],
                       "factors": info["factors"], "solves": info["solves"], "prFeas": info["prFeas"],
                       "duFeas": info["duFeas"], "muFeas": info["muFeas"], "pobj": info["pobj"], "dobj": info["dobj"],
                       "driver": "cip_ipm_solve (native)"}

@@ -299,15 +299,20 @@ end
 # function, so a method on it that consults the override routes every stock call site -- including the one
 # `optimize!` reaches through `preprocess_conicIP` -- to the engine while a `ConicIPB200.Optimizer` is solving,
 # and falls back to the stock QR solver otherwise.
-const _stock_qr = ConicIP.kktsolver_qr
+# The stock method is reached through the world age recorded just before the route is installed
+# (`Base.invoke_in_world`): binding `ConicIP.kktsolver_qr` to a constant would not do, because redefining the
+# method changes what that very function object calls.
+const STOCK_WORLD = Ref{UInt}(typemax(UInt))
 function routed_kktsolver(Q, A, G, cone_dims)
     k = KKTSOLVER_OVERRIDE[]
-    return k === nothing ? _stock_qr(Q, A, G, cone_dims) : k(Q, A, G, cone_dims)
+    k === nothing || return k(Q, A, G, cone_dims)
+    return Base.invoke_in_world(STOCK_WORLD[], ConicIP.kktsolver_qr, Q, A, G, cone_dims)
 end
-# Installing the route is one assignment in ConicIP's namespace (done once, at `using ConicIPB200`); with the
+# Installing the route is one method definition in ConicIP's namespace (done once, at `using ConicIPB200`); with the
 # patch of (1) applied it is unnecessary and skipped.
 function __init__()
     if !(:kktsolver in fieldnames(ConicIP.Optimizer))
+        STOCK_WORLD[] = Base.get_world_counter()
         @eval ConicIP kktsolver_qr(Q, A, G, cone_dims) = $(routed_kktsolver)(Q, A, G, cone_dims)
     end
 end

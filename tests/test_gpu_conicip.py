@@ -177,3 +177,58 @@ def test_infeasible_with_linear_constraints():
     assert s.status == so.status == "Infeasible"
     sn = cb.conicIP_native(H, c, np.eye(n), np.zeros(n), [("R", n)], G, np.array([-1.0]), optTol=1e-7)
     assert sn.status == "Infeasible" and np.all(np.isnan(sn.y))
+
+
+def _b200_plugin_for_reference_loop(Q, A, G, cone_dims):
+    """`kktsolver = kktsolver_b200` as the REFERENCE's host loop sees it: LEVEL 1 once, then every LEVEL-2 call hands
+    over a host `Block` of Diagonal / SymWoodbury / VecCongurance blocks (here the oracle's classes, translated to the
+    binding's -- in Julia they are ConicIP's own types and `flatten` reads them directly) and every LEVEL-3 call
+    host vectors.  Nothing else of the loop touches the GPU: this is the drop-in of BASELINE's north star."""
+    import conicip_b200 as cb
+    gen = cb.kktsolver_b200(Q, A, G if G.shape[0] else None, cone_dims)
+
+    def solve3x3gen(F, F_invT):
+        blocks = []
+        for B in F.blocks:
+            if isinstance(B, O.Diag):
+                blocks.append(cb.Diagonal(B.diag))
+            elif isinstance(B, O.SymWoodbury):
+                blocks.append(cb.SymWoodbury(B.Adiag, B.B, B.D))
+            else:
+                blocks.append(cb.VecCongurance(B.R))
+        return gen(cb.Block(blocks), None)
+    return solve3x3gen
+
+
+@pytest.mark.parametrize("which", ["mixed", "sdp_mix"])
+def test_reference_host_loop_with_b200_kktsolver_plugin(which):
+    """The literal drop-in: the restated reference loop (oracle.conicIP, src/ConicIP.jl:468-939: host vectors, host
+    cone arithmetic) with ONLY its `kktsolver` keyword replaced by the B200 engine through the three-level protocol
+    (src/ConicIP.jl:667,682,688), against the same loop with the stock solvers."""
+    if which == "mixed":
+        prob = P.mixed()
+        stock = O.pivot(O.kktsolver_2x2)
+    else:
+        rng = np.random.default_rng(3)
+        k, n = 6, 25
+        dim = k * (k + 1) // 2
+        cones = [("R", 9), ("S", dim), ("Q", 5)]
+        m = 9 + dim + 5
+        A = rng.standard_normal((m, n)) / np.sqrt(n)
+        s0 = np.zeros(m)
+        s0[:9] = rng.uniform(0.2, 1.2, 9)
+        B = rng.standard_normal((k, k))
+        s0[9:9 + dim] = O.vecm(B @ B.T / k + 0.5 * np.eye(k))
+        u = 0.1 * rng.standard_normal(4)
+        s0[9 + dim] = 1 + np.linalg.norm(u); s0[10 + dim:] = u
+        y0 = rng.standard_normal(n)
+        G = rng.standard_normal((2, n)) / np.sqrt(n)
+        prob = dict(Q=np.eye(n), c=rng.standard_normal(n), A=A, b=A @ y0 - s0, cone_dims=cones, G=G, d=G @ y0)
+        stock = O.kktsolver_qr                     # the stock solver that is right for VecCongurance blocks
+    args = (prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"])
+    so = O.conicIP(*args, optTol=1e-8, kktsolver=stock)
+    sb = O.conicIP(*args, optTol=1e-8, kktsolver=_b200_plugin_for_reference_loop)
+    assert sb.status == so.status == "Optimal" and abs(sb.Iter - so.Iter) <= 1
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    assert rel(sb.y, so.y) < 1e-6 and rel(sb.v, so.v) < 1e-6 and rel(sb.w, so.w) < 1e-6
+    assert max(sb.prFeas, sb.duFeas, sb.muFeas) < 1e-8

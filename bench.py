@@ -598,6 +598,20 @@ def run_b200(args, n, m):
                       "factors": info["factors"], "solves": info["solves"], "prFeas": info["prFeas"],
                       "duFeas": info["duFeas"], "muFeas": info["muFeas"], "pobj": info["pobj"], "dobj": info["dobj"],
                       "driver": "cip_ipm_solve (native)"}
+        if hprob is not None and D.world == 1 and ngpus_single == 1:
+            # the host-driven path beside the native loop: conicip_b200.conicIP is the reference's loop structure
+            # (src/ConicIP.jl:468-939) on the host, calling LEVEL 1 / 2 / 3 and every cone kernel through the C ABI one
+            # call at a time -- what a host driver that keeps `conicIP` pays; the time includes LEVEL 1 (the upload)
+            t_host = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                hs = cb.conicIP(hprob["Q"], hprob["c"], hprob["A"], hprob["b"], hprob["cone_dims"],
+                                hprob["G"] if p else None, hprob["d"] if p else None, optTol=1e-8)
+                t_host.append(time.perf_counter() - t0)
+            solve_info["host_driver"] = {"time_to_1e-8_s": min(t_host), "first_call_s": t_host[0], "status": hs.status,
+                                         "iterations": hs.Iter, "factors": hs.factors, "solves": hs.solves,
+                                         "driver": "conicip_b200.conicIP (host loop, one C-ABI call per kktsolver level and cone kernel; includes cip_create)"}
         if parity is not None:
             # the solution itself, to compare across the N = 1, 2, 4, 8 lines, and an independent evaluation of the
             # optimality conditions of  min 1/2 y'Qy - c'y  s.t. Ay - b in K  through the mat-vec kernels

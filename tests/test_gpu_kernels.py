@@ -72,6 +72,9 @@ CASES = {
     "tiny": dict(n=1, mr=1, ncones=0, k=2, p=0, seed=8),
     "n_multi_tile": dict(n=520, mr=640, ncones=8, k=17, p=1, seed=9),
     "tall_skinny": dict(n=200, mr=20000, ncones=40, k=33, p=3, seed=10),   # 3 C tiles, 667 k tiles: split-K SYRK
+    # equality block of five row tiles on eleven column panels: the two-level Schur substitution (p > 384), with a
+    # partial last outer panel
+    "big_equality_block": dict(n=1300, mr=1500, ncones=3, k=9, p=520, seed=14),
 }
 
 

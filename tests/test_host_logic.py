@@ -193,3 +193,44 @@ def test_shard_plan_matches_python_mirror():
                 if t != "R":
                     assert any(lo <= off and off + k <= hi for lo, hi in plan), (t, k, plan)
                 off += k
+
+
+def test_bench_host_problem_c5_and_cpu_unit():
+    """The host side of `bench.py --config C5` at a reduced size: the MOI-shaped LP with an S block of order 64, the
+    synthetic interior points (S rows: vecm of a positive definite matrix) and one CPU unit through the oracle."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_mod"] = bench
+    spec.loader.exec_module(bench)
+    prob, pts, rhs = bench.host_problem("C5", 2200, 2200 + 2080)
+    assert prob["cone_dims"] == [("R", 2200), ("S", 2080)] and prob["A"].shape == (4280, 2200) and prob["G"].shape[0] > 0
+    for v, s in pts:
+        for x in (v, s):
+            assert x[:2200].min() > 0 and np.linalg.eigvalsh(O.mat(x[2200:])).min() > 0
+    assert len(rhs) == bench.NSOLVES
+    assert 0 < bench.cpu_unit_oracle(prob, pts, rhs, repeats=1) < 120
+
+
+def test_ncu_traffic_table_matches_the_committed_captures():
+    """`roofline.traffic` comes from profiles/ncu_traffic.json; every entry that names a committed raw ncu page must
+    be reproducible from that page (scripts/ncu_traffic.py), i.e. the number is read from a capture, not typed in."""
+    import importlib.util
+    import json
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ncu_traffic", os.path.join(root, "scripts", "ncu_traffic.py"))
+    nt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nt)
+    tab = json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))
+    checked = 0
+    for key, ent in tab.items():
+        m = re.match(r"(profiles/\S+_raw\.csv)", ent["source"])
+        if not m:
+            continue
+        d = nt.read_raw(os.path.join(root, m.group(1)))[0]
+        assert abs(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] - ent["dram_bytes"]) <= 1e-6 * ent["dram_bytes"], key
+        checked += 1
+    assert checked >= 2 and "gemm_nt_syrk:n=16384,m=262144" in tab

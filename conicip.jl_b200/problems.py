@@ -66,6 +66,27 @@ def soc_direct():
     return _prob("soc_direct", Q, c, A, b, [("Q", 4), ("R", n)], optTol=1e-6)
 
 
+def moi_simple_lp():
+    """`Simple LP via MOI` (test/runtests.jl:684-715) as the wrapper hands it to conicIP (src/MOI_wrapper.jl:142-285):
+    min x1 + x2  s.t.  x1 + x2 >= 1, x >= 0; objective 1, x = (0.5, 0.5) (analytic centre of the optimal face)."""
+    A = np.array([[1.0, 1.0], [1.0, 0.0], [0.0, 1.0]])
+    return _prob("moi_simple_lp", np.zeros((2, 2)), -np.array([1.0, 1.0]), A, np.array([1.0, 0.0, 0.0]), [("R", 3)], optTol=1e-6)
+
+
+def moi_soc():
+    """`SOC via MOI` (test/runtests.jl:717-744): min x3  s.t.  x1 = 1, x2 = 1, ||(x1, x2)|| <= x3; x3 = sqrt(2)."""
+    A = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    G = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    return _prob("moi_soc", np.zeros((3, 3)), -np.array([0.0, 0.0, 1.0]), A, np.zeros(3), [("Q", 3)], G, np.array([1.0, 1.0]),
+                 optTol=1e-6)
+
+
+def moi_max_sense():
+    """`Max sense via MOI` (test/runtests.jl:746-775): max x1 + 2 x2  s.t.  x1 + x2 <= 1, x >= 0; objective 2, x = (0, 1)."""
+    A = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    return _prob("moi_max_sense", np.zeros((2, 2)), np.array([1.0, 2.0]), A, np.array([-1.0, 0.0, 0.0]), [("R", 3)], optTol=1e-6)
+
+
 def infeasible(n=10, seed=0):
     """test/runtests.jl:441-460 (shape only; data from NumPy's RNG)."""
     rng = np.random.default_rng(seed)

@@ -232,3 +232,21 @@ def test_reference_host_loop_with_b200_kktsolver_plugin(which):
     rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
     assert rel(sb.y, so.y) < 1e-6 and rel(sb.v, so.v) < 1e-6 and rel(sb.w, so.w) < 1e-6
     assert max(sb.prFeas, sb.duFeas, sb.muFeas) < 1e-8
+
+
+@pytest.mark.parametrize("name,obj,x,xtol", [("moi_simple_lp", 1.0, [0.5, 0.5], 1e-2), ("moi_soc", np.sqrt(2.0), [1.0, 1.0, np.sqrt(2.0)], 1e-4),
+                                             ("moi_max_sense", -2.0, [0.0, 1.0], 1e-2)])
+def test_moi_wrapper_problems_on_the_device(name, obj, x, xtol):
+    """test/runtests.jl:684-775 -- the LP, SOC and max-sense problems of the MOI wrapper tests (Q = 0) through both
+    drivers: the reference's expected values, and the oracle's iterates."""
+    import conicip_b200 as cb
+    prob = getattr(P, name)()
+    args = (prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"] if prob["G"].shape[0] else None,
+            prob["d"] if prob["G"].shape[0] else None)
+    so = O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"], optTol=1e-6,
+                   kktsolver=O.pivot(O.kktsolver_2x2))
+    for solve in (cb.conicIP_native, cb.conicIP):
+        s = solve(*args, optTol=1e-6)
+        assert s.status == so.status == "Optimal" and abs(s.Iter - so.Iter) <= 1
+        assert abs(-prob["c"] @ s.y - obj) < 1e-4 and np.abs(s.y - np.array(x)).max() < xtol
+        assert np.linalg.norm(s.y - so.y) < 1e-6 * max(1.0, np.linalg.norm(so.y))

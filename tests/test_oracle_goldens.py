@@ -142,3 +142,16 @@ def test_committed_golden_fixture_matches_oracle():
         assert s.status == g["status"] and s.Iter == g["Iter"]
         assert np.allclose(s.y, g["y"], rtol=1e-7, atol=1e-9)
         assert abs(s.Mu - g["Mu"]) <= 1e-6 * abs(g["Mu"])
+
+
+@pytest.mark.parametrize("name,obj,x,xtol", [("moi_simple_lp", 1.0, [0.5, 0.5], 1e-2), ("moi_soc", np.sqrt(2.0), [1.0, 1.0, np.sqrt(2.0)], 1e-4),
+                                             ("moi_max_sense", -2.0, [0.0, 1.0], 1e-2)])
+def test_moi_wrapper_problems(name, obj, x, xtol):
+    """test/runtests.jl:684-775 -- the three problems of the MOI wrapper tests in the form the wrapper hands to conicIP
+    (Q = 0; src/MOI_wrapper.jl:142-285), with the reference's expected objective (atol 1e-4) and primal values."""
+    prob = getattr(P, name)()
+    for ks in SOLVERS.values():
+        s = O.conicIP(prob["Q"], prob["c"], prob["A"], prob["b"], prob["cone_dims"], prob["G"], prob["d"], optTol=1e-6, kktsolver=ks)
+        assert s.status == "Optimal"
+        assert abs(-prob["c"] @ s.y - obj) < 1e-4            # conicIP minimises 1/2 y'Qy - c'y
+        assert np.abs(s.y - np.array(x)).max() < xtol
